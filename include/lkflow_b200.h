@@ -1,0 +1,124 @@
+/*
+ * lkflow_b200.h -- C ABI of the B200-native optical-flow hot path (liblkflow_b200.so).
+ *
+ * The reference (chiahuilin0531/LK-Optical-Flow-Method) has no FFI of its own: its hot path is the set
+ * of cv2 Python calls made by VP_detection_using_optical_flow.py ("VP.py") and LK_Final.py ("LKF.py").
+ * Each entry point below names the call site(s) it replaces.  All image / point pointers are DEVICE
+ * pointers (HBM) unless an argument is explicitly called host_*; the caller owns every buffer; the
+ * library owns only the opaque workspace `lkf_ctx`.  Every call enqueues work on `stream`
+ * (a cudaStream_t passed as void*) and returns without synchronising, so a sequence of calls can be
+ * captured in a CUDA graph.  Return value: 0 on success, a negative lkf_status otherwise.  No C++
+ * exceptions cross this boundary.  One ctx per (device, stream); calls on one ctx are not re-entrant.
+ *
+ * Data layout: images are pitched, batched planes.  Pixel (b, y, x, c) of an image lives at
+ *   data + b*image_pitch + y*row_pitch + (x*channels + c)*sizeof(element)      (pitches in BYTES).
+ * Pyramid level l of a WxH image has size ((W+1)>>1 applied l times, same for H) and NO border
+ * (REFLECT_101 is applied by index mirroring inside the kernels).
+ */
+#ifndef LKFLOW_B200_H
+#define LKFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LKF_ABI_VERSION 1
+#define LKF_MAX_LEVELS 8
+
+typedef enum lkf_status {
+    LKF_OK = 0,
+    LKF_ERR_ARG = -1,          /* bad argument (what cv2 rejects with an assertion)              */
+    LKF_ERR_CUDA = -2,         /* a CUDA runtime call failed; see lkf_last_error()               */
+    LKF_ERR_UNSUPPORTED = -3,  /* valid for cv2 but outside this path (SURVEY 8b "never exercised") */
+    LKF_ERR_NOMEM = -4,
+    LKF_ERR_OVERFLOW = -5      /* a caller-provided capacity was too small                        */
+} lkf_status;
+
+typedef struct lkf_ctx lkf_ctx;    /* opaque workspace (scratch buffers, device properties) */
+typedef void *lkf_stream;          /* cudaStream_t */
+
+typedef struct lkf_image {
+    void *data;                    /* device pointer */
+    int32_t batch, height, width, channels;
+    int64_t row_pitch;             /* bytes between rows   */
+    int64_t image_pitch;           /* bytes between images */
+} lkf_image;
+
+/* cv2 constants used by the scripts (VP.py:100, VP.py:406) */
+#define LKF_TERM_CRITERIA_COUNT 1
+#define LKF_TERM_CRITERIA_EPS 2
+#define LKF_OPTFLOW_USE_INITIAL_FLOW 4
+#define LKF_OPTFLOW_LK_GET_MIN_EIGENVALS 8
+
+/* lk_params of VP.py:98-100 / LKF.py:96-98 plus the two cv2 defaults the scripts do not pass */
+typedef struct lkf_lk_params {
+    int32_t win_w, win_h;          /* winSize (15,15)                                   */
+    int32_t max_level;             /* maxLevel 2 (0-based; reduced like cv2 when too small) */
+    int32_t crit_type;             /* TERM_CRITERIA_EPS | TERM_CRITERIA_COUNT           */
+    int32_t max_count;             /* 10                                                */
+    int32_t flags;                 /* 0                                                 */
+    double epsilon;                /* 0.03 (squared inside, like cv2)                   */
+    double min_eig_threshold;      /* 1e-4                                              */
+} lkf_lk_params;
+
+/* feature_params of VP.py:92-95 / LKF.py:90-93 */
+typedef struct lkf_gftt_params {
+    int32_t max_corners;           /* <=0: unlimited (bounded by the output capacity)   */
+    int32_t block_size;            /* 7 in the scripts, cv2 default 3                   */
+    int32_t dy_tail_cols;          /* -1: W mod 32 (cv2 4.13 AVX-512 host rule) */
+    int32_t reserved;
+    double quality_level;          /* 0.3                                               */
+    double min_distance;           /* 7                                                 */
+} lkf_gftt_params;
+
+/* ---- library / workspace ------------------------------------------------------------------ */
+int lkf_abi_version(void);
+const char *lkf_strerror(int status);
+const char *lkf_last_error(void);                 /* text of the last CUDA failure on this thread */
+int lkf_ctx_create(int device, lkf_ctx **out);
+void lkf_ctx_destroy(lkf_ctx *ctx);
+/* number of kernels launched through this ctx since creation (bench.py "gpu_launches") */
+int64_t lkf_ctx_launch_count(const lkf_ctx *ctx);
+
+/* ---- a1: cv.cvtColor(img, cv.COLOR_BGR2GRAY)            VP.py:406, LKF.py:402 -------------- */
+int lkf_bgr2gray_u8(const lkf_image *bgr, const lkf_image *gray, lkf_stream stream);
+/* ---- a2: cv.GaussianBlur(img, (3,3), 0)                 VP.py:420, LKF.py:416 -------------- */
+int lkf_gaussian_blur3_u8(const lkf_image *src, const lkf_image *dst, lkf_stream stream);
+/* ---- a1+a2 fused: process_img()                         VP.py:404-425, LKF.py:400-421 ------ */
+int lkf_process_img_u8(const lkf_image *bgr, const lkf_image *dst, lkf_stream stream);
+/* ---- a3: one pyrDown step of the pyramid cv.calcOpticalFlowPyrLK builds   VP.py:545 -------- */
+int lkf_pyr_down_u8(const lkf_image *src, const lkf_image *dst, lkf_stream stream);
+/* ---- a4: Scharr Ix/Iy (int16 x2 interleaved) of one level, as PyrLK computes it  VP.py:545 -- */
+int lkf_scharr_s16(const lkf_image *src, const lkf_image *dst_ixiy, lkf_stream stream);
+/* levels cv2 really uses for a WxH image (maxLevel is reduced when a level would be <= winSize) */
+int lkf_effective_max_level(int height, int width, int win_w, int win_h, int max_level);
+
+/* ---- a7: the tracker of cv.calcOpticalFlowPyrLK(prev, next, p0, None, **lk_params)  VP.py:545-546,
+ *      LKF.py:531-532.  prev_pyr/next_pyr: arrays of (n_levels) descriptors, level 0 first, all with
+ *      the same batch B.  Points are padded per image: prev_pts[b][i] for i < pt_counts[b]
+ *      (pt_counts == NULL: every image has max_pts points).  next_pts is also an input when
+ *      LKF_OPTFLOW_USE_INITIAL_FLOW is set.  status/err follow cv2 ((N,1) u8 / f32); err of a
+ *      status-0 point is 0.  iters (nullable) receives executed LK iterations per point. */
+int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *params, int n_levels,
+                     const lkf_image *prev_pyr, const lkf_image *next_pyr,
+                     const float *prev_pts, const int32_t *pt_counts, int max_pts,
+                     float *next_pts, uint8_t *status, float *err, int32_t *iters,
+                     lkf_stream stream);
+
+/* ---- a5: cornerMinEigenVal inside cv.goodFeaturesToTrack          VP.py:503,707 ------------- */
+int lkf_corner_min_eigen_f32(const lkf_image *src_u8, const lkf_image *eig_f32, int block_size,
+                             int dy_tail_cols, lkf_stream stream);
+/* ---- a6: selection part of cv.goodFeaturesToTrack(img, mask=, **feature_params)  VP.py:503,707.
+ *      eig: B planes; mask (nullable): n_masks planes per image or shared (mask->batch == n_masks
+ *      or B*n_masks).  For image b and mask m the result is corners[(b*n_masks+m)][0..count) as
+ *      (x,y) float32, strongest first, and counts[b*n_masks+m].  max_out = row capacity. */
+int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *params, const lkf_image *eig_f32,
+                    const lkf_image *mask_u8, int n_masks, float *corners, int32_t *counts,
+                    int max_out, lkf_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LKFLOW_B200_H */

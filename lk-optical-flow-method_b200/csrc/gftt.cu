@@ -1,0 +1,360 @@
+// gftt.cu -- a5/a6: cv.goodFeaturesToTrack (VP.py:503,707; LKF.py:488,691).
+//   a5  cornerMinEigenVal: Sobel3 (float32, cv2's exact op order) -> dx^2, dxdy, dy^2 -> block x block box SUM in
+//       FP64 -> lambda_min in unfused float32                       (oracle lko_min_eigen)
+//   a6  masked max -> threshold -> 3x3 non-max suppression -> compaction (warp ballots) -> sort by
+//       (value desc, raster index desc) -> greedy min-distance on a cell grid, in score order
+//                                                                    (oracle lko_gftt_select)
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// a5: min-eigenvalue map.  Output tile 64 x 16; u8 tile with (r0+1, r1+1) halo; products at the
+// REFLECTED coordinate (a product outside the image is the product AT the mirrored pixel, not the
+// Sobel of the mirrored image: dxdy changes sign and the dy row pass is not mirror-symmetric in fp32).
+// ---------------------------------------------------------------------------------------------
+constexpr int ME_W = 64, ME_H = 16, ME_NT = 256;
+
+__global__ void __launch_bounds__(ME_NT)
+k_min_eigen(const uint8_t *__restrict__ src, long long rp, long long ip, int H, int W, float *__restrict__ dst,
+            long long drp, long long dip, int bs, int tail_cols, float s, float s2)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int r0 = bs / 2;                        // window = [-r0, bs-1-r0]
+    const int pw = ME_W + bs - 1, ph = ME_H + bs - 1;     // product tile
+    const int uw = pw + 2, uh = ph + 2;                   // u8 tile
+    const int uws = (uw + 3) & ~3;
+    double *hs = reinterpret_cast<double *>(smem);                           // [3][ph][ME_W]
+    float *prod = reinterpret_cast<float *>(hs + 3 * ph * ME_W);            // [3][ph][pw]
+    uint8_t *u8 = reinterpret_cast<uint8_t *>(prod + 3 * ph * pw);          // [uh][uws]
+    const int x0 = blockIdx.x * ME_W, y0 = blockIdx.y * ME_H, b = blockIdx.z;
+    const uint8_t *img = src + (long long)b * ip;
+    const int ux0 = x0 - r0 - 1, uy0 = y0 - r0 - 1;
+    for (int i = threadIdx.x; i < uh * uw; i += ME_NT) {
+        int r = i / uw, c = i - r * uw;
+        u8[r * uws + c] = img[(long long)reflect101(uy0 + r, H) * rp + reflect101(ux0 + c, W)];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ph * pw; i += ME_NT) {
+        int r = i / pw, c = i - r * pw;
+        // true coordinate of this product, and its position in the u8 tile
+        int qx = reflect101(x0 - r0 + c, W), qy = reflect101(y0 - r0 + r, H);
+        int tx = qx - ux0, ty = qy - uy0;
+        // mirrored coordinates of far-out tile cells (beyond what any output needs) may leave the tile
+        if (tx < 1 || tx > uw - 2 || ty < 1 || ty > uh - 2) { prod[i] = 0.f; prod[ph * pw + i] = 0.f; prod[2 * ph * pw + i] = 0.f; continue; }
+        const uint8_t *p0 = u8 + (ty - 1) * uws + tx, *p1 = p0 + uws, *p2 = p1 + uws;
+        // Dx: row pass r = I[x+1]-I[x-1] (exact), column pass fma(s, r[y-1]+r[y+1], s2*r[y])
+        float ra = (float)((int)p0[1] - (int)p0[-1]), rb = (float)((int)p1[1] - (int)p1[-1]), rc = (float)((int)p2[1] - (int)p2[-1]);
+        float dx = __fmaf_rn(s, __fadd_rn(ra, rc), __fmul_rn(s2, rb));
+        // Dy: row pass smoothing (vector body fused, scalar tail unfused), column pass row[y+1]-row[y-1]
+        float top, bot;
+        if (qx < W - tail_cols) {
+            top = __fmaf_rn(s, (float)p0[1], __fmaf_rn(s2, (float)p0[0], __fmul_rn(s, (float)p0[-1])));
+            bot = __fmaf_rn(s, (float)p2[1], __fmaf_rn(s2, (float)p2[0], __fmul_rn(s, (float)p2[-1])));
+        } else {
+            top = __fadd_rn(__fadd_rn(__fmul_rn(s, (float)p0[-1]), __fmul_rn(s2, (float)p0[0])), __fmul_rn(s, (float)p0[1]));
+            bot = __fadd_rn(__fadd_rn(__fmul_rn(s, (float)p2[-1]), __fmul_rn(s2, (float)p2[0])), __fmul_rn(s, (float)p2[1]));
+        }
+        float dy = __fsub_rn(bot, top);
+        prod[i] = __fmul_rn(dx, dx);
+        prod[ph * pw + i] = __fmul_rn(dx, dy);
+        prod[2 * ph * pw + i] = __fmul_rn(dy, dy);
+    }
+    __syncthreads();
+    // horizontal box sums in FP64
+    for (int i = threadIdx.x; i < ph * ME_W; i += ME_NT) {
+        int r = i / ME_W, c = i - r * ME_W;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float *p = prod + k * ph * pw + r * pw + c;
+            double acc = 0.0;
+            for (int j = 0; j < bs; j++) acc = __dadd_rn(acc, (double)p[j]);
+            hs[k * ph * ME_W + i] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ME_H * ME_W; i += ME_NT) {
+        int r = i / ME_W, c = i - r * ME_W;
+        int x = x0 + c, y = y0 + r;
+        if (x >= W || y >= H) continue;
+        double sa = 0.0, sb = 0.0, sc = 0.0;
+        for (int j = 0; j < bs; j++) {
+            sa = __dadd_rn(sa, hs[(r + j) * ME_W + c]);
+            sb = __dadd_rn(sb, hs[ph * ME_W + (r + j) * ME_W + c]);
+            sc = __dadd_rn(sc, hs[2 * ph * ME_W + (r + j) * ME_W + c]);
+        }
+        float a = __fmul_rn((float)sa, 0.5f), bb = (float)sb, c2 = __fmul_rn((float)sc, 0.5f);
+        float t = __fsub_rn(a, c2);
+        float v = __fsub_rn(__fadd_rn(a, c2), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(bb, bb))));
+        *reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(dst) + (long long)b * dip + (long long)y * drp + 4LL * x) = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a6 helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2key(float f)
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // order-preserving; 0 is below every float
+}
+__device__ __forceinline__ float key2f(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+constexpr int MAXM = 8;      // masks per image handled in one pass
+
+struct MaskSet {
+    const uint8_t *p; long long rp, ip; int per_image;   // per_image: 1 -> plane index b*n_masks+m, 0 -> m
+};
+
+__global__ void __launch_bounds__(256)
+k_masked_max(const float *__restrict__ eig, long long erp, long long eip, int H, int W, MaskSet ms, int n_masks,
+             unsigned *__restrict__ maxkey)
+{
+    const int b = blockIdx.y;
+    const unsigned char *e = reinterpret_cast<const unsigned char *>(eig) + (long long)b * eip;
+    unsigned best[MAXM];
+#pragma unroll
+    for (int m = 0; m < MAXM; m++) best[m] = 0;
+    const long long P = (long long)H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        int y = (int)(i / W), x = (int)(i - (long long)y * W);
+        unsigned k = f2key(*reinterpret_cast<const float *>(e + (long long)y * erp + 4LL * x));
+#pragma unroll
+        for (int m = 0; m < MAXM; m++) {
+            if (m >= n_masks) break;
+            bool on = true;
+            if (ms.p) on = ms.p[(long long)(ms.per_image ? b * n_masks + m : m) * ms.ip + (long long)y * ms.rp + x] != 0;
+            if (on && k > best[m]) best[m] = k;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MAXM; m++) {
+        if (m >= n_masks) break;
+        unsigned v = __reduce_max_sync(0xffffffffu, best[m]);
+        if ((threadIdx.x & 31) == 0 && v) atomicMax(&maxkey[b * n_masks + m], v);
+    }
+}
+
+// threshold + 3x3 NMS + compaction: one candidate list per (image, mask)
+__global__ void __launch_bounds__(256)
+k_nms_compact(const float *__restrict__ eig, long long erp, long long eip, int H, int W, MaskSet ms, int n_masks,
+              const unsigned *__restrict__ maxkey, double quality, unsigned long long *__restrict__ keys,
+              int *__restrict__ counts, int cap)
+{
+    const int b = blockIdx.z;
+    const int x = 1 + blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = 1 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    const unsigned char *e = reinterpret_cast<const unsigned char *>(eig) + (long long)b * eip;
+    bool inside = x < W - 1 && y < H - 1;
+    float v = 0.f;
+    bool is_max = false;
+    if (inside) {
+        const float *r0 = reinterpret_cast<const float *>(e + (long long)(y - 1) * erp) + x;
+        const float *r1 = reinterpret_cast<const float *>(e + (long long)y * erp) + x;
+        const float *r2 = reinterpret_cast<const float *>(e + (long long)(y + 1) * erp) + x;
+        v = r1[0];
+        float m = fmaxf(fmaxf(fmaxf(r0[-1], r0[0]), fmaxf(r0[1], r1[-1])), fmaxf(fmaxf(r1[1], r2[-1]), fmaxf(r2[0], r2[1])));
+        is_max = v >= m;
+    }
+    for (int m = 0; m < n_masks; m++) {
+        const int list = b * n_masks + m;
+        unsigned mk = maxkey[list];
+        double max_val = mk ? (double)key2f(mk) : 0.0;
+        float thr = (float)(max_val * quality);
+        bool cand = inside && is_max && v > thr;          // v > thr >= ... ; thresholded neighbours are <= v
+        if (cand && ms.p) cand = ms.p[(long long)(ms.per_image ? list : m) * ms.ip + (long long)y * ms.rp + x] != 0;
+        // a thresholded map keeps v only if v > thr; "v != 0" then holds unless thr < 0 and v == 0
+        if (cand && v == 0.f) cand = false;
+        unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (bal) {
+            int lane = threadIdx.x & 31, leader = __ffs(bal) - 1, base = 0;
+            if (lane == leader) base = atomicAdd(&counts[list], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (cand) {
+                int pos = base + __popc(bal & ((1u << lane) - 1));
+                if (pos < cap)
+                    keys[(long long)list * cap + pos] = ((unsigned long long)f2key(v) << 32) | (unsigned)(y * W + x);
+            }
+        }
+    }
+}
+
+// sort (bitonic, one CTA per list, keys in global/L2) + greedy min-distance (warp 0), SURVEY A.5 (5)-(7)
+constexpr int SS_NT = 1024;
+
+__global__ void __launch_bounds__(SS_NT)
+k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__ counts, int cap, int W, int H,
+              int max_corners, double min_distance, int cell, int gw, int gh, uint32_t *__restrict__ grid_all,
+              float *__restrict__ corners, int32_t *__restrict__ out_counts, int max_out)
+{
+    const int list = blockIdx.x;
+    unsigned long long *keys = keys_all + (long long)list * cap;
+    int n = counts[list];
+    const bool overflow = n > cap;
+    if (overflow) n = cap;
+    int npad = 32;
+    while (npad < n) npad <<= 1;
+    for (int i = n + threadIdx.x; i < npad; i += SS_NT) keys[i] = 0ull;
+    // the cell grid: 4 slots per cell, each 0xffffffff (empty) or (y<<16|x)
+    uint32_t *grid = grid_all + (size_t)list * gw * gh * 4;
+    if (min_distance >= 1)
+        for (int i = threadIdx.x; i < gw * gh * 4; i += SS_NT) grid[i] = 0xffffffffu;
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npad; i += SS_NT) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = keys[i], c = keys[ixj];
+                    bool desc = (i & k) == 0;
+                    if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    float *out = corners + (size_t)list * max_out * 2;
+    int nc = 0;
+    const int limit = (max_corners > 0 && max_corners < max_out) ? max_corners : max_out;
+    bool truncated = false;
+    if (min_distance >= 1) {
+        const double md2 = min_distance * min_distance;
+        bool done = false;
+        for (int base = 0; base < n && !done; base += 32) {
+            int i = base + lane;
+            bool good = i < n;
+            int x = 0, y = 0;
+            if (good) {
+                unsigned idx = (unsigned)(keys[i] & 0xffffffffull);
+                y = idx / W; x = idx - y * W;
+                int xc = x / cell, yc = y / cell;
+                int x1 = max(0, xc - 1), y1 = max(0, yc - 1), x2 = min(gw - 1, xc + 1), y2 = min(gh - 1, yc + 1);
+                for (int yy = y1; yy <= y2 && good; yy++)
+                    for (int xx = x1; xx <= x2 && good; xx++) {
+                        const uint4 sl = *reinterpret_cast<const uint4 *>(grid + (size_t)(yy * gw + xx) * 4);
+                        const uint32_t s[4] = {sl.x, sl.y, sl.z, sl.w};
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (s[q] != 0xffffffffu) {
+                                float dx = (float)(x - (int)(s[q] & 0xffff)), dy = (float)(y - (int)(s[q] >> 16));
+                                if ((double)(dx * dx + dy * dy) < md2) good = false;
+                            }
+                    }
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, good);
+            while (bal) {
+                int leader = __ffs(bal) - 1;
+                int lx = __shfl_sync(0xffffffffu, x, leader), ly = __shfl_sync(0xffffffffu, y, leader);
+                if (lane == leader) {
+                    uint32_t *c = grid + (size_t)((y / cell) * gw + (x / cell)) * 4;
+                    int q = 0;
+                    while (q < 3 && c[q] != 0xffffffffu) q++;
+                    c[q] = ((uint32_t)y << 16) | (uint32_t)x;
+                    if (nc < max_out) { out[2 * nc] = (float)x; out[2 * nc + 1] = (float)y; }
+                    good = false;
+                }
+                nc++;
+                if (nc == limit) { done = true; if (max_corners <= 0 || max_corners > max_out) truncated = true; break; }
+                if (good) {
+                    float dx = (float)(x - lx), dy = (float)(y - ly);
+                    if (abs(x / cell - lx / cell) <= 1 && abs(y / cell - ly / cell) <= 1 && (double)(dx * dx + dy * dy) < md2)
+                        good = false;
+                }
+                bal = __ballot_sync(0xffffffffu, good);
+            }
+            __syncwarp();
+        }
+    } else {
+        int take = n < limit ? n : limit;
+        for (int i = lane; i < take; i += 32) {
+            unsigned idx = (unsigned)(keys[i] & 0xffffffffull);
+            int y = idx / W, x = idx - y * W;
+            out[2 * i] = (float)x; out[2 * i + 1] = (float)y;
+        }
+        nc = take;
+        if (n > limit && (max_corners <= 0 || max_corners > max_out)) truncated = true;
+    }
+    // negative count = capacity problem (candidate scratch or output rows too small): host raises
+    if (lane == 0) out_counts[list] = (overflow || truncated) ? -1 - nc : nc;
+}
+
+}  // namespace
+
+LKF_EXPORT int lkf_corner_min_eigen_f32(const lkf_image *src, const lkf_image *eig, int block_size, int dy_tail_cols,
+                                        lkf_stream stream)
+{
+    if (!img_ok(src, 1, 1) || !img_ok(eig, 1, 4) || src->batch != eig->batch || src->height != eig->height ||
+        src->width != eig->width || !aligned_to(eig, 4))
+        return LKF_ERR_ARG;
+    if (block_size < 1) return LKF_ERR_ARG;
+    if (block_size > 31) return LKF_ERR_UNSUPPORTED;
+    const int H = src->height, W = src->width, bs = block_size;
+    if (dy_tail_cols < 0) dy_tail_cols = W % 32;
+    const double scale = 1.0 / (4.0 * bs * 255.0);           // (1 << (ksize-1)) * blockSize * 255, ksize = 3
+    const float s = (float)scale, s2 = (float)(2.0 * scale);
+    const int pw = ME_W + bs - 1, ph = ME_H + bs - 1, uw = pw + 2, uh = ph + 2, uws = (uw + 3) & ~3;
+    size_t smem = (size_t)3 * ph * ME_W * 8 + (size_t)3 * ph * pw * 4 + (size_t)uh * uws;
+    if (smem > 48 * 1024) LKF_CUDA(cudaFuncSetAttribute(k_min_eigen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((W + ME_W - 1) / ME_W, (H + ME_H - 1) / ME_H, src->batch);
+    k_min_eigen<<<grid, ME_NT, smem, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch, H, W,
+                                                            (float *)eig->data, eig->row_pitch, eig->image_pitch, bs,
+                                                            dy_tail_cols, s, s2);
+    LKF_LAUNCH_CHECK(nullptr);
+    return LKF_OK;
+}
+
+LKF_EXPORT int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *eig, const lkf_image *mask,
+                               int n_masks, float *corners, int32_t *counts, int max_out, lkf_stream stream)
+{
+    if (!ctx || !p || !img_ok(eig, 1, 4) || !aligned_to(eig, 4) || !corners || !counts || max_out < 1) return LKF_ERR_ARG;
+    if (!(p->quality_level > 0) || p->min_distance < 0) return LKF_ERR_ARG;          // cv2 asserts
+    if (n_masks < 1 || n_masks > MAXM) return LKF_ERR_ARG;
+    const int B = eig->batch, H = eig->height, W = eig->width;
+    MaskSet ms{nullptr, 0, 0, 0};
+    if (mask) {
+        if (!img_ok(mask, 1, 1) || mask->height != H || mask->width != W) return LKF_ERR_ARG;
+        if (mask->batch == n_masks) ms.per_image = 0;
+        else if (mask->batch == B * n_masks) ms.per_image = 1;
+        else return LKF_ERR_ARG;
+        ms.p = (const uint8_t *)mask->data; ms.rp = mask->row_pitch; ms.ip = mask->image_pitch;
+    } else if (n_masks != 1) return LKF_ERR_ARG;
+    if (H < 3 || W < 3) {        // no interior pixel: no corner
+        LKF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * B * n_masks, (cudaStream_t)stream));
+        return LKF_OK;
+    }
+    const int lists = B * n_masks;
+    const long long P = (long long)H * W;
+    long long cap_ll = P / 4 + 4096;
+    int cap = 32;
+    while (cap < cap_ll) cap <<= 1;
+    int cell = 1, gw = 1, gh = 1;
+    if (p->min_distance >= 1) {
+        cell = (int)nearbyint(p->min_distance);
+        gw = (W + cell - 1) / cell; gh = (H + cell - 1) / cell;
+    }
+    void *keys, *cnt, *grid;
+    int rc;
+    if ((rc = lkf_scratch(ctx, 0, (size_t)lists * cap * 8, &keys)) != LKF_OK) return rc;
+    if ((rc = lkf_scratch(ctx, 1, (size_t)lists * 2 * sizeof(int), &cnt)) != LKF_OK) return rc;
+    if ((rc = lkf_scratch(ctx, 2, (size_t)lists * gw * gh * 16, &grid)) != LKF_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned *maxkey = (unsigned *)cnt;
+    int *ccount = (int *)cnt + lists;
+    LKF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)lists * 2 * sizeof(int), s));
+    int chunks = (int)((P + 256 * 8 - 1) / (256 * 8));
+    if (chunks > 4 * ctx->sm_count) chunks = 4 * ctx->sm_count;
+    k_masked_max<<<dim3(chunks, B), 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, maxkey);
+    LKF_LAUNCH_CHECK(ctx);
+    dim3 g2((W - 2 + 31) / 32, (H - 2 + 7) / 8, B);
+    k_nms_compact<<<g2, 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, maxkey,
+                                     p->quality_level, (unsigned long long *)keys, ccount, cap);
+    LKF_LAUNCH_CHECK(ctx);
+    k_sort_select<<<lists, SS_NT, 0, s>>>((unsigned long long *)keys, ccount, cap, W, H, p->max_corners, p->min_distance, cell, gw,
+                                         gh, (uint32_t *)grid, corners, counts, max_out);
+    LKF_LAUNCH_CHECK(ctx);
+    return LKF_OK;
+}

@@ -1,0 +1,297 @@
+// stencil.cu -- a1 BGR->gray, a2 3x3 Gaussian, a1+a2 fused, a3 pyrDown, a4 Scharr (materialised).
+// All integer, bit-exact against cv2 4.13 (formulas: SURVEY.md Appendix A.1-A.3; oracle: oracle/lkflow_oracle.c).
+// Structure: shared-memory tiles with halos, 4-byte aligned bodies loaded as 32-bit words, REFLECT_101 by
+// index mirroring (the mirror source of a 1..2-px halo is always inside the image).
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+// ---------------------------------------------------------------------------------------------
+// Tile loaders.  A tile row in shared memory holds WORDS 32-bit words; column c of the row is image
+// column xs + c (xs is a multiple of 4).  Rows ys .. ys+ROWS-1 (mirrored).
+// ---------------------------------------------------------------------------------------------
+struct SrcU8 {
+    const uint8_t *p; long long rp; int H, W; bool al4;
+    __device__ __forceinline__ uint32_t word(int y, int gx) const
+    {
+        const uint8_t *row = p + (long long)y * rp;
+        if (al4 && gx >= 0 && gx + 3 < W) return *reinterpret_cast<const uint32_t *>(row + gx);
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v |= (uint32_t)row[reflect101(gx + j, W)] << (8 * j);
+        return v;
+    }
+};
+// gray computed on the fly from interleaved BGR (fused a1+a2)
+struct SrcBGR {
+    const uint8_t *p; long long rp; int H, W; bool al4;
+    __device__ __forceinline__ uint32_t word(int y, int gx) const
+    {
+        const uint8_t *row = p + (long long)y * rp;
+        if (al4 && gx >= 0 && gx + 3 < W) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(row + 3 * gx);
+            uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+            // bytes: a = B0 G0 R0 B1 | b = G1 R1 B2 G2 | c = R2 B3 G3 R3
+            uint32_t g0 = gray_of(a & 255, (a >> 8) & 255, (a >> 16) & 255);
+            uint32_t g1 = gray_of(a >> 24, b & 255, (b >> 8) & 255);
+            uint32_t g2 = gray_of((b >> 16) & 255, b >> 24, c & 255);
+            uint32_t g3 = gray_of((c >> 8) & 255, (c >> 16) & 255, c >> 24);
+            return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+        }
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint8_t *px = row + 3 * reflect101(gx + j, W);
+            v |= gray_of(px[0], px[1], px[2]) << (8 * j);
+        }
+        return v;
+    }
+};
+
+template <int ROWS, int WORDS, class Src>
+__device__ __forceinline__ void load_tile(const Src &s, int xs, int ys, uint32_t (*sm)[WORDS])
+{
+    for (int i = threadIdx.x; i < ROWS * WORDS; i += NT) {
+        int r = i / WORDS, k = i - r * WORDS;
+        sm[r][k] = s.word(reflect101(ys + r, s.H), xs + 4 * k);
+    }
+}
+
+__device__ __forceinline__ void store4(uint8_t *row, int x, int W, bool al4, uint32_t v)
+{
+    if (al4 && x + 3 < W) *reinterpret_cast<uint32_t *>(row + x) = v;
+    else
+        for (int j = 0; j < 4 && x + j < W; j++) row[x + j] = (uint8_t)(v >> (8 * j));
+}
+
+// ---------------------------------------------------------------------------------------------
+// a1: BGR -> gray, 16 px (48 B in, 16 B out) per thread when 16-byte aligned, else 4 px / scalar.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_bgr2gray(Img src, Img dst, int al16, int al4)
+{
+    const int y = blockIdx.y, b = blockIdx.z;
+    const uint8_t *srow = src.p + (long long)b * src.ip + (long long)y * src.rp;
+    uint8_t *drow = dst.p + (long long)b * dst.ip + (long long)y * dst.rp;
+    const int W = src.W;
+    int x = (blockIdx.x * NT + threadIdx.x) * 16;
+    if (x >= W) return;
+    if (al16 && x + 16 <= W) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(srow + 3 * x);
+        uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+        uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t a = w[3 * k], bb = w[3 * k + 1], c = w[3 * k + 2];
+            uint32_t g0 = gray_of(a & 255, (a >> 8) & 255, (a >> 16) & 255);
+            uint32_t g1 = gray_of(a >> 24, bb & 255, (bb >> 8) & 255);
+            uint32_t g2 = gray_of((bb >> 16) & 255, bb >> 24, c & 255);
+            uint32_t g3 = gray_of((c >> 8) & 255, (c >> 16) & 255, c >> 24);
+            o[k] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+        }
+        *reinterpret_cast<uint4 *>(drow + x) = make_uint4(o[0], o[1], o[2], o[3]);
+        return;
+    }
+    SrcBGR s{srow, 0, 1, W, al4 != 0};
+    for (int k = 0; k < 4 && x + 4 * k < W; k++) store4(drow, x + 4 * k, W, al4 != 0, s.word(0, x + 4 * k));
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2 / a1+a2: 3x3 [1 2 1]^2, (sum+8)>>4, tile 128 x 32 out, 1-px halo.  Each thread: 4 px x 4 rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int BT_W = 128, BT_H = 32;
+constexpr int BT_WORDS = BT_W / 4 + 2;          // one pad word each side (halo lives in it)
+
+template <class Src>
+__global__ void __launch_bounds__(NT) k_blur3(Src src0, long long src_ip, Img dst, int dst_al4)
+{
+    __shared__ uint32_t sm[BT_H + 2][BT_WORDS];
+    const int x0 = blockIdx.x * BT_W, y0 = blockIdx.y * BT_H, b = blockIdx.z;
+    Src s = src0;
+    s.p += (long long)b * src_ip;
+    load_tile<BT_H + 2, BT_WORDS>(s, x0 - 4, y0 - 1, sm);
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 32 x 8 threads, 4 rows each
+    const int x = x0 + 4 * tx;
+    if (x >= dst.W) return;
+    // horizontal sums h[r][j] = p[x+j-1] + 2 p[x+j] + p[x+j+1] for the 6 rows feeding 4 output rows
+    uint32_t h[6][4];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        const uint32_t *row = sm[4 * ty + r];
+        uint32_t l = row[tx], m = row[tx + 1], rr = row[tx + 2];
+        uint32_t p[6] = {l >> 24, m & 255, (m >> 8) & 255, (m >> 16) & 255, m >> 24, rr & 255};
+#pragma unroll
+        for (int j = 0; j < 4; j++) h[r][j] = p[j] + 2 * p[j + 1] + p[j + 2];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int y = y0 + 4 * ty + r;
+        if (y >= dst.H) break;
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v |= ((h[r][j] + 2 * h[r + 1][j] + h[r + 2][j] + 8) >> 4) << (8 * j);
+        store4(dst.p + (long long)b * dst.ip + (long long)y * dst.rp, x, dst.W, dst_al4 != 0, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a3: pyrDown 5x5 [1 4 6 4 1]^2, (sum+128)>>8, even source coordinates.  Output tile 64 x 16.
+// ---------------------------------------------------------------------------------------------
+constexpr int PD_W = 64, PD_H = 16;
+constexpr int PD_SROWS = 2 * PD_H + 3;           // source rows 2*y0-2 .. 2*(y0+PD_H-1)+2
+constexpr int PD_SWORDS = (2 * PD_W + 8) / 4;    // source cols 2*x0-4 .. 2*x0+2*PD_W+3
+
+__global__ void __launch_bounds__(NT) k_pyrdown(SrcU8 src0, long long src_ip, Img dst, int dst_al4)
+{
+    __shared__ uint32_t sm[PD_SROWS][PD_SWORDS];
+    __shared__ uint16_t hs[PD_SROWS][PD_W];
+    const int x0 = blockIdx.x * PD_W, y0 = blockIdx.y * PD_H, b = blockIdx.z;
+    SrcU8 s = src0;
+    s.p += (long long)b * src_ip;
+    load_tile<PD_SROWS, PD_SWORDS>(s, 2 * x0 - 4, 2 * y0 - 2, sm);
+    __syncthreads();
+    // horizontal pass: out col xo reads source cols 2xo-2..2xo+2 = tile cols 2(xo-x0)+2 .. +6
+    for (int i = threadIdx.x; i < PD_SROWS * (PD_W / 2); i += NT) {
+        int r = i / (PD_W / 2), k = i - r * (PD_W / 2);     // k: pair of outputs (2k, 2k+1)
+        const uint32_t *row = sm[r];
+        uint32_t a = row[k], m = row[k + 1], c = row[k + 2];
+        // tile cols 4k .. 4k+11 ; outputs 2k -> cols 4k+2..4k+6 ; 2k+1 -> cols 4k+4..4k+8
+        uint32_t p2 = (a >> 16) & 255, p3 = a >> 24, p4 = m & 255, p5 = (m >> 8) & 255, p6 = (m >> 16) & 255,
+                 p7 = m >> 24, p8 = c & 255;
+        hs[r][2 * k] = (uint16_t)(p2 + 4 * p3 + 6 * p4 + 4 * p5 + p6);
+        hs[r][2 * k + 1] = (uint16_t)(p4 + 4 * p5 + 6 * p6 + 4 * p7 + p8);
+    }
+    __syncthreads();
+    // vertical pass: 4 consecutive outputs per thread
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16
+    const int x = x0 + 4 * tx, y = y0 + ty;
+    if (x >= dst.W || y >= dst.H) return;
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int c = 4 * tx + j;
+        uint32_t sacc = hs[2 * ty][c] + 4u * hs[2 * ty + 1][c] + 6u * hs[2 * ty + 2][c] + 4u * hs[2 * ty + 3][c] +
+                        hs[2 * ty + 4][c];
+        v |= ((sacc + 128) >> 8) << (8 * j);
+    }
+    store4(dst.p + (long long)b * dst.ip + (long long)y * dst.rp, x, dst.W, dst_al4 != 0, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a4: Scharr, int16 (Ix,Iy) interleaved, unnormalised; tile 128 x 32, 1-px halo (as the blur).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_scharr(SrcU8 src0, long long src_ip, Img dst, int dst_al16)
+{
+    __shared__ uint32_t sm[BT_H + 2][BT_WORDS];
+    const int x0 = blockIdx.x * BT_W, y0 = blockIdx.y * BT_H, b = blockIdx.z;
+    SrcU8 s = src0;
+    s.p += (long long)b * src_ip;
+    load_tile<BT_H + 2, BT_WORDS>(s, x0 - 4, y0 - 1, sm);
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x = x0 + 4 * tx;
+    if (x >= dst.W) return;
+    int p[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        const uint32_t *row = sm[4 * ty + r];
+        uint32_t l = row[tx], m = row[tx + 1], rr = row[tx + 2];
+        p[r][0] = l >> 24; p[r][1] = m & 255; p[r][2] = (m >> 8) & 255; p[r][3] = (m >> 16) & 255;
+        p[r][4] = m >> 24; p[r][5] = rr & 255;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int y = y0 + 4 * ty + r;
+        if (y >= dst.H) break;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int sp = 3 * p[r][j + 2] + 10 * p[r + 1][j + 2] + 3 * p[r + 2][j + 2];
+            int sn = 3 * p[r][j] + 10 * p[r + 1][j] + 3 * p[r + 2][j];
+            int ix = sp - sn;
+            int iy = 3 * (p[r + 2][j] - p[r][j]) + 10 * (p[r + 2][j + 1] - p[r][j + 1]) + 3 * (p[r + 2][j + 2] - p[r][j + 2]);
+            o[j] = ((uint32_t)ix & 0xffffu) | ((uint32_t)iy << 16);
+        }
+        uint8_t *drow = dst.p + (long long)b * dst.ip + (long long)y * dst.rp;
+        if (dst_al16 && x + 3 < dst.W) *reinterpret_cast<uint4 *>(drow + 4 * x) = make_uint4(o[0], o[1], o[2], o[3]);
+        else
+            for (int j = 0; j < 4 && x + j < dst.W; j++) *reinterpret_cast<uint32_t *>(drow + 4 * (x + j)) = o[j];
+    }
+}
+
+bool same_geometry(const lkf_image *a, const lkf_image *b)
+{
+    return a->batch == b->batch && a->height == b->height && a->width == b->width;
+}
+
+}  // namespace
+
+LKF_EXPORT int lkf_bgr2gray_u8(const lkf_image *bgr, const lkf_image *gray, lkf_stream stream)
+{
+    if (!img_ok(bgr, 3, 1) || !img_ok(gray, 1, 1) || !same_geometry(bgr, gray)) return LKF_ERR_ARG;
+    Img s = to_img(bgr), d = to_img(gray);
+    int al16 = aligned_to(bgr, 16) && aligned_to(gray, 16), al4 = aligned_to(bgr, 4) && aligned_to(gray, 4);
+    dim3 grid((s.W + 16 * NT - 1) / (16 * NT), s.H, s.B);
+    k_bgr2gray<<<grid, NT, 0, (cudaStream_t)stream>>>(s, d, al16, al4);
+    LKF_LAUNCH_CHECK(nullptr);
+    return LKF_OK;
+}
+
+LKF_EXPORT int lkf_gaussian_blur3_u8(const lkf_image *src, const lkf_image *dst, lkf_stream stream)
+{
+    if (!img_ok(src, 1, 1) || !img_ok(dst, 1, 1) || !same_geometry(src, dst) || src->data == dst->data) return LKF_ERR_ARG;
+    Img d = to_img(dst);
+    SrcU8 s{(const uint8_t *)src->data, src->row_pitch, src->height, src->width, aligned_to(src, 4)};
+    dim3 grid((d.W + BT_W - 1) / BT_W, (d.H + BT_H - 1) / BT_H, d.B);
+    k_blur3<SrcU8><<<grid, NT, 0, (cudaStream_t)stream>>>(s, src->image_pitch, d, aligned_to(dst, 4));
+    LKF_LAUNCH_CHECK(nullptr);
+    return LKF_OK;
+}
+
+LKF_EXPORT int lkf_process_img_u8(const lkf_image *bgr, const lkf_image *dst, lkf_stream stream)
+{
+    if (!img_ok(bgr, 3, 1) || !img_ok(dst, 1, 1) || !same_geometry(bgr, dst)) return LKF_ERR_ARG;
+    Img d = to_img(dst);
+    SrcBGR s{(const uint8_t *)bgr->data, bgr->row_pitch, bgr->height, bgr->width, aligned_to(bgr, 4)};
+    dim3 grid((d.W + BT_W - 1) / BT_W, (d.H + BT_H - 1) / BT_H, d.B);
+    k_blur3<SrcBGR><<<grid, NT, 0, (cudaStream_t)stream>>>(s, bgr->image_pitch, d, aligned_to(dst, 4));
+    LKF_LAUNCH_CHECK(nullptr);
+    return LKF_OK;
+}
+
+LKF_EXPORT int lkf_pyr_down_u8(const lkf_image *src, const lkf_image *dst, lkf_stream stream)
+{
+    if (!img_ok(src, 1, 1) || !img_ok(dst, 1, 1) || src->batch != dst->batch ||
+        dst->height != (src->height + 1) / 2 || dst->width != (src->width + 1) / 2)
+        return LKF_ERR_ARG;
+    Img d = to_img(dst);
+    SrcU8 s{(const uint8_t *)src->data, src->row_pitch, src->height, src->width, aligned_to(src, 4)};
+    dim3 grid((d.W + PD_W - 1) / PD_W, (d.H + PD_H - 1) / PD_H, d.B);
+    k_pyrdown<<<grid, NT, 0, (cudaStream_t)stream>>>(s, src->image_pitch, d, aligned_to(dst, 4));
+    LKF_LAUNCH_CHECK(nullptr);
+    return LKF_OK;
+}
+
+LKF_EXPORT int lkf_scharr_s16(const lkf_image *src, const lkf_image *dst, lkf_stream stream)
+{
+    if (!img_ok(src, 1, 1) || !img_ok(dst, 2, 2) || !same_geometry(src, dst) || !aligned_to(dst, 4)) return LKF_ERR_ARG;
+    Img d = to_img(dst);
+    SrcU8 s{(const uint8_t *)src->data, src->row_pitch, src->height, src->width, aligned_to(src, 4)};
+    dim3 grid((d.W + BT_W - 1) / BT_W, (d.H + BT_H - 1) / BT_H, d.B);
+    k_scharr<<<grid, NT, 0, (cudaStream_t)stream>>>(s, src->image_pitch, d, aligned_to(dst, 16));
+    LKF_LAUNCH_CHECK(nullptr);
+    return LKF_OK;
+}
+
+LKF_EXPORT int lkf_effective_max_level(int height, int width, int win_w, int win_h, int max_level)
+{
+    int w = width, h = height;
+    for (int level = 0; level <= max_level; level++) {
+        w = (w + 1) / 2; h = (h + 1) / 2;
+        if (w <= win_w || h <= win_h) return level;
+    }
+    return max_level;
+}

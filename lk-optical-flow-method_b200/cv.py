@@ -1,0 +1,220 @@
+"""Drop-in replacement for the cv2 calls on the reference's hot path.
+
+Use at the reference's call sites as  ``import lk_optical_flow_method_b200.cv as cv``  (or call
+``patch(cv2)`` to swap the four functions inside an already imported cv2 module).  Same names,
+argument meaning, return conventions and error behaviour as the cv2 functions the scripts call:
+
+    cvtColor(img, COLOR_BGR2GRAY)                                  VP.py:406   LKF.py:402
+    GaussianBlur(img, (3,3), 0)                                    VP.py:420   LKF.py:416
+    goodFeaturesToTrack(img, mask=..., **feature_params)           VP.py:503,707  LKF.py:488,691
+    calcOpticalFlowPyrLK(prev, next, p0, None, **lk_params)        VP.py:545-546  LKF.py:531-532
+
+Host inputs (numpy arrays / CPU tensors) are copied to the device, processed by the CUDA kernels and
+copied back (numpy in -> numpy out, writable, like cv2).  CUDA tensors are processed in place on the
+current stream and CUDA tensors are returned without synchronising.  Anything cv2 accepts that the
+scripts never exercise raises `error` instead of mis-computing.  Every other attribute
+(VideoCapture, fillPoly, circle, ...) is forwarded to the real cv2 when it is installed, so an
+unmodified script keeps working; none of those are on the hot path.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import LkfError
+from .device import as_host_array, is_device, require_cuda
+
+COLOR_BGR2GRAY = 6
+TERM_CRITERIA_COUNT = 1
+TERM_CRITERIA_MAX_ITER = 1
+TERM_CRITERIA_EPS = 2
+OPTFLOW_USE_INITIAL_FLOW = 4
+OPTFLOW_LK_GET_MIN_EIGENVALS = 8
+BORDER_DEFAULT = 4
+BORDER_REFLECT_101 = 4
+
+
+class error(Exception):
+    """Counterpart of cv2.error for argument checks of the replaced functions."""
+
+
+def _dev():
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_dev(a, dtype=None):
+    """host array -> CUDA tensor on the current stream."""
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(_dev(), non_blocking=True)
+
+
+def _back(t, like):
+    """CUDA tensor -> same kind of host object as `like` (numpy array or CPU tensor)."""
+    h = t.cpu()                      # synchronises the current stream
+    return h.numpy() if isinstance(like, np.ndarray) else h
+
+
+def _check_u8_image(img, name, channels=None):
+    if img is None:
+        raise error(f"{name} is None")
+    shape = tuple(img.shape)
+    dt = img.dtype
+    if dt not in (np.uint8, torch.uint8):
+        raise error(f"{name}: only 8-bit images are supported on this path (got {dt})")
+    if channels == 1 and len(shape) != 2:
+        raise error(f"{name}: expected a single-channel HxW image, got shape {shape}")
+    if channels == 3 and (len(shape) != 3 or shape[2] != 3):
+        raise error(f"{name}: expected HxWx3, got shape {shape}")
+    if shape[0] < 1 or shape[1] < 1:
+        raise error(f"{name}: empty image")
+
+
+def cvtColor(src, code, dst=None, dstCn=0):
+    """cv2.cvtColor for code == COLOR_BGR2GRAY (VP.py:406)."""
+    if code != COLOR_BGR2GRAY:
+        raise error("cvtColor: only COLOR_BGR2GRAY is implemented on this path")
+    _check_u8_image(src, "src", 3)
+    if is_device(src):
+        return ops.bgr2gray(src)[0]
+    host = as_host_array(src)
+    return _back(ops.bgr2gray(_to_dev(host))[0], src)
+
+
+def GaussianBlur(src, ksize, sigmaX, dst=None, sigmaY=0, borderType=BORDER_DEFAULT):
+    """cv2.GaussianBlur for ksize == (3,3), sigma == 0, BORDER_DEFAULT (VP.py:420)."""
+    if tuple(ksize) != (3, 3) or sigmaX != 0 or sigmaY != 0 or borderType != BORDER_DEFAULT:
+        raise error("GaussianBlur: only ksize=(3,3), sigma=0, BORDER_DEFAULT is implemented on this path")
+    _check_u8_image(src, "src", 1)
+    if is_device(src):
+        return ops.gaussian_blur3(src)[0]
+    host = as_host_array(src)
+    return _back(ops.gaussian_blur3(_to_dev(host))[0], src)
+
+
+def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, corners=None, mask=None, blockSize=3,
+                        useHarrisDetector=False, k=0.04, gradientSize=3):
+    """cv2.goodFeaturesToTrack (VP.py:503,707): (N,1,2) float32 corners, strongest first, or None."""
+    if useHarrisDetector or gradientSize != 3:
+        raise error("goodFeaturesToTrack: useHarrisDetector / gradientSize != 3 are not on this path")
+    _check_u8_image(image, "image", 1)
+    if not (qualityLevel > 0) or minDistance < 0:
+        raise error("goodFeaturesToTrack: qualityLevel > 0 && minDistance >= 0 required")
+    if maxCorners < 0:
+        raise error("goodFeaturesToTrack: maxCorners >= 0 required")
+    if blockSize < 1 or blockSize > 31:
+        raise error("goodFeaturesToTrack: blockSize must be in 1..31 on this path")
+    H, W = image.shape
+    if mask is not None:
+        if tuple(mask.shape) != (H, W) or mask.dtype not in (np.uint8, torch.uint8):
+            raise error("goodFeaturesToTrack: mask must be CV_8UC1 of the image size")
+    on_dev = is_device(image)
+    img_d = image if on_dev else _to_dev(as_host_array(image))
+    mask_d = None
+    if mask is not None:
+        mask_d = mask if is_device(mask) else _to_dev(as_host_array(mask))
+    max_out = int(maxCorners) if maxCorners > 0 else max(1, (H * W) // 4)
+    eig = ops.min_eigen(img_d, blockSize)
+    cor, cnt = ops.gftt_select(eig, mask_d, maxCorners, qualityLevel, minDistance, max_out)
+    n = int(cnt[0].item())                     # one sync: the count decides the output shape
+    if n < 0:
+        raise error("goodFeaturesToTrack: corner capacity exceeded")
+    if n == 0:
+        return None
+    res = cor[0, :n].reshape(n, 1, 2)
+    return res.clone() if on_dev else _back(res, image)
+
+
+def _norm_points(p, name):
+    if p is None:
+        return None, None
+    shape = tuple(p.shape)
+    if p.dtype not in (np.float32, torch.float32):
+        raise error(f"{name}: points must be float32 (cv2: checkVector(2, CV_32F))")
+    ok = (len(shape) == 2 and shape[1] == 2) or (len(shape) == 3 and shape[2] == 2 and (shape[0] == 1 or shape[1] == 1))
+    if not ok:
+        raise error(f"{name}: expected (N,1,2), (1,N,2) or (N,2) float32, got {shape}")
+    if isinstance(p, np.ndarray):
+        if not p.flags["C_CONTIGUOUS"]:
+            raise error(f"{name}: points must be contiguous")
+    elif not p.is_contiguous():
+        raise error(f"{name}: points must be contiguous")
+    return shape, int(np.prod(shape)) // 2
+
+
+def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status=None, err=None, winSize=(21, 21), maxLevel=3,
+                         criteria=(TERM_CRITERIA_COUNT | TERM_CRITERIA_EPS, 30, 0.01), flags=0,
+                         minEigThreshold=1e-4):
+    """cv2.calcOpticalFlowPyrLK (VP.py:545-546): -> (nextPts like prevPts, status (N,1) u8, err (N,1) f32);
+    (None, None, None) for zero points."""
+    _check_u8_image(prevImg, "prevImg", 1)
+    _check_u8_image(nextImg, "nextImg", 1)
+    if tuple(prevImg.shape) != tuple(nextImg.shape):
+        raise error("calcOpticalFlowPyrLK: prevImg and nextImg must have the same size")
+    if not (winSize[0] > 2 and winSize[1] > 2):
+        raise error("calcOpticalFlowPyrLK: winSize.width > 2 && winSize.height > 2 required")
+    if maxLevel < 0:
+        raise error("calcOpticalFlowPyrLK: maxLevel >= 0 required")
+    if flags & ~(OPTFLOW_USE_INITIAL_FLOW | OPTFLOW_LK_GET_MIN_EIGENVALS):
+        raise error("calcOpticalFlowPyrLK: unknown flags")
+    shape, n = _norm_points(prevPts, "prevPts")
+    if shape is None:
+        raise error("calcOpticalFlowPyrLK: prevPts is None")
+    if n == 0:
+        return None, None, None
+    if flags & OPTFLOW_USE_INITIAL_FLOW:
+        nshape, nn = _norm_points(nextPts, "nextPts")
+        if nshape is None or nn != n:
+            raise error("calcOpticalFlowPyrLK: OPTFLOW_USE_INITIAL_FLOW needs nextPts of the same size")
+    H, W = prevImg.shape
+    on_dev = is_device(prevPts)
+    prev_d = prevImg if is_device(prevImg) else _to_dev(as_host_array(prevImg))
+    next_d = nextImg if is_device(nextImg) else _to_dev(as_host_array(nextImg))
+    pts_d = (prevPts if on_dev else _to_dev(as_host_array(prevPts))).reshape(1, n, 2)
+    init_d = None
+    if flags & OPTFLOW_USE_INITIAL_FLOW:
+        init_d = (nextPts if is_device(nextPts) else _to_dev(as_host_array(nextPts))).reshape(1, n, 2)
+    n_levels = ops.effective_levels(H, W, winSize, maxLevel)
+    params = ops.lk_params_struct(winSize, maxLevel, criteria, flags, minEigThreshold)
+    try:
+        ppyr = ops.build_pyramid(prev_d, n_levels)
+        npyr = ops.build_pyramid(next_d, n_levels)
+        nxt, st, er = ops.pyrlk(ppyr, npyr, pts_d, params, next_pts=init_d)
+    except LkfError as e:
+        raise error(str(e)) from e
+    nxt = nxt.reshape(shape)
+    st = st.reshape(n, 1)
+    er = er.reshape(n, 1)
+    if on_dev:
+        return nxt, st, er
+    host = torch.cat([nxt.reshape(-1), er.reshape(-1), st.reshape(-1).to(torch.float32)]).cpu().numpy()
+    p1 = host[:2 * n].reshape(shape).copy()
+    e1 = host[2 * n:3 * n].reshape(n, 1).copy()
+    s1 = host[3 * n:].astype(np.uint8).reshape(n, 1)
+    if isinstance(prevPts, np.ndarray):
+        return p1, s1, e1
+    return torch.from_numpy(p1), torch.from_numpy(s1), torch.from_numpy(e1)
+
+
+def patch(cv2_module):
+    """Replace the four hot-path functions inside an imported cv2 module (returns the originals)."""
+    saved = {}
+    for name in ("cvtColor", "GaussianBlur", "goodFeaturesToTrack", "calcOpticalFlowPyrLK"):
+        saved[name] = getattr(cv2_module, name)
+        setattr(cv2_module, name, globals()[name])
+    return saved
+
+
+def unpatch(cv2_module, saved):
+    for name, fn in saved.items():
+        setattr(cv2_module, name, fn)
+
+
+def __getattr__(name):
+    # not on the hot path: forward to the real OpenCV when present (VideoCapture, fillPoly, ...)
+    try:
+        import cv2
+    except ImportError as e:
+        raise AttributeError(f"{name!r} is not part of the B200 hot path and cv2 is not installed") from e
+    return getattr(cv2, name)

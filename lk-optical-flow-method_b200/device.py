@@ -1,0 +1,113 @@
+"""Device-side plumbing: torch tensors as HBM buffers, image descriptors, per-device workspace.
+
+PyTorch is used for memory, streams and (in bench.py) torch.distributed only; every arithmetic step
+is a kernel of liblkflow_b200.so called through the C ABI (see _lib.py).
+"""
+import ctypes
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LkfImage, check
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("lk_optical_flow_method_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback")
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_ELEM = {torch.uint8: 1, torch.int16: 2, torch.float32: 4}
+
+
+def image_desc(t, channels=1):
+    """LkfImage for a CUDA tensor shaped [B,H,W], [H,W] (channels==1 or packed last dim) or
+    [B,H,W,C] / [H,W,C].  Rows must be dense (stride of x == C elements); row/image pitch are free."""
+    if not t.is_cuda:
+        raise ValueError("expected a CUDA tensor")
+    es = _ELEM[t.dtype]
+    if channels == 1:
+        if t.dim() == 2:
+            t = t.unsqueeze(0)
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise ValueError("expected [B,H,W] with unit x stride")
+        B, H, W = t.shape
+    else:
+        if t.dim() == 3:
+            t = t.unsqueeze(0)
+        if t.dim() != 4 or t.shape[3] != channels or t.stride(3) != 1 or t.stride(2) != channels:
+            raise ValueError(f"expected [B,H,W,{channels}] interleaved")
+        B, H, W, _ = t.shape
+    return LkfImage(t.data_ptr(), B, H, W, channels, t.stride(1) * es, t.stride(0) * es)
+
+
+def as_host_array(x):
+    """numpy view of a host input (numpy array or CPU torch tensor)."""
+    if isinstance(x, np.ndarray):
+        return x
+    if isinstance(x, torch.Tensor) and not x.is_cuda:
+        return x.numpy()
+    raise TypeError(f"unsupported host array type {type(x)!r}")
+
+
+def is_device(x):
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+class Workspace:
+    """One per (device): the opaque lkf_ctx plus cached device buffers keyed by (tag, shape, dtype)."""
+
+    _tls = threading.local()
+
+    def __init__(self, device):
+        require_cuda()
+        self.device = torch.device("cuda", device)
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        check(self.lib.lkf_ctx_create(device, ctypes.byref(h)), "lkf_ctx_create")
+        self.ctx = h
+        self._bufs = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                self.lib.lkf_ctx_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    def buf(self, tag, shape, dtype, pitch_align=None):
+        key = (tag, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def launches(self):
+        return int(self.lib.lkf_ctx_launch_count(None))
+
+    @classmethod
+    def current(cls):
+        require_cuda()
+        dev = torch.cuda.current_device()
+        d = getattr(cls._tls, "ws", None)
+        if d is None:
+            d = cls._tls.ws = {}
+        if dev not in d:
+            d[dev] = cls(dev)
+        return d[dev]
+
+
+def pyramid_shapes(H, W, n_levels):
+    out = [(H, W)]
+    for _ in range(1, n_levels):
+        H, W = (H + 1) // 2, (W + 1) // 2
+        out.append((H, W))
+    return out
