@@ -118,6 +118,9 @@ int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *params, const lkf_image
                     const lkf_image *mask_u8, int n_masks, float *corners, int32_t *counts,
                     int max_out, lkf_stream stream);
 
+/* ---- measurement helper (bench.py): FFMA-rate probe; executes blocks*256*iters*16 flops ------- */
+int lkf_probe_fp32_fma(int blocks, int iters, float *out, lkf_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

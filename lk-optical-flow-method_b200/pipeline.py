@@ -1,0 +1,163 @@
+"""Device-resident frame-pair pipeline (the throughput path of BASELINE.json's metric).
+
+One *step* processes B frame pairs of a clip held in HBM: for every new BGR frame
+    process_img (a1+a2 fused) -> pyramid (a3) ,
+then for every pair (frame i-1 -> frame i)
+    pyramidal LK (a4 on the fly + a7)  on that pair's points,
+and, on every `refresh_every`-th pair, goodFeaturesToTrack (a5+a6) on the pair's previous frame whose
+corners replace that pair's points -- the REPlace refresh of VP.py:700-718 (TP_UPDATE_TIME = 10).
+Frame i's pyramid serves as `next` of pair i and `prev` of pair i+1, so each frame is processed once
+(the scripts' cv2 calls rebuild both pyramids on every call, VP.py:545).
+
+All launches go to the current CUDA stream without host synchronisation; `capture()` records the step
+into a CUDA graph.
+"""
+import torch
+
+from . import ops
+from .device import Workspace, pyramid_shapes
+
+
+class PairPipeline:
+    def __init__(self, B, H, W, n_pts, lk_params=None, gftt_params=None, refresh_every=10, device=None):
+        self.B, self.H, self.W, self.N = int(B), int(H), int(W), int(n_pts)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lk = dict(winSize=(21, 21), maxLevel=2, criteria=(3, 10, 0.03), flags=0, minEigThreshold=1e-4)
+        if lk_params:
+            self.lk.update(lk_params)
+        self.gftt = dict(maxCorners=self.N, qualityLevel=0.01, minDistance=7, blockSize=7)
+        if gftt_params:
+            self.gftt.update(gftt_params)
+        self.refresh_every = int(refresh_every)
+        self.n_levels = ops.effective_levels(H, W, self.lk["winSize"], self.lk["maxLevel"])
+        self.params = ops.lk_params_struct(**self.lk)
+        self.ws = Workspace.current()
+        # pyramid slots 0..B : slot 0 = last frame of the previous step
+        self.levels = [torch.zeros((self.B + 1, h, w), dtype=torch.uint8, device=self.dev)
+                       for (h, w) in pyramid_shapes(H, W, self.n_levels)]
+        self.pts = torch.zeros((self.B, self.N, 2), dtype=torch.float32, device=self.dev)
+        self.counts = torch.full((self.B,), self.N, dtype=torch.int32, device=self.dev)
+        self.next_pts = torch.zeros_like(self.pts)
+        self.status = torch.zeros((self.B, self.N), dtype=torch.uint8, device=self.dev)
+        self.err = torch.zeros((self.B, self.N), dtype=torch.float32, device=self.dev)
+        self.iters = None
+        self.R = len(range(0, self.B, self.refresh_every)) if self.refresh_every > 0 else 0
+        if self.R:
+            self.eig = torch.zeros((self.R, H, W), dtype=torch.float32, device=self.dev)
+            self.corners = torch.zeros((self.R, self.N, 2), dtype=torch.float32, device=self.dev)
+            self.ccounts = torch.zeros((self.R,), dtype=torch.int32, device=self.dev)
+        self.graph = None
+
+    # -- state -----------------------------------------------------------------------------------
+    def prime(self, first_bgr):
+        """Process the frame preceding the first pair into slot 0 ([H,W,3] uint8 CUDA tensor)."""
+        ops.process_img(first_bgr[None] if first_bgr.dim() == 3 else first_bgr, out=self.levels[0][0:1])
+        for l in range(1, self.n_levels):
+            ops.pyr_down(self.levels[l - 1][0:1], out=self.levels[l][0:1])
+
+    def set_points(self, pts, counts=None):
+        self.pts.copy_(pts)
+        if counts is not None:
+            self.counts.copy_(counts)
+
+    # -- stages (each is one kernel launch or a fixed short sequence) -----------------------------
+    def stage_process(self, bgr):
+        ops.process_img(bgr, out=self.levels[0][1:])
+
+    def stage_pyramid(self):
+        for l in range(1, self.n_levels):
+            ops.pyr_down(self.levels[l - 1][1:], out=self.levels[l][1:])
+
+    def stage_refresh(self):
+        if not self.R:
+            return
+        e = self.refresh_every
+        ops.min_eigen(self.levels[0][0:self.B:e], self.gftt["blockSize"], out=self.eig)
+        ops.gftt_select(self.eig, None, self.gftt["maxCorners"], self.gftt["qualityLevel"], self.gftt["minDistance"],
+                        self.N, out=(self.corners, self.ccounts))
+        self.pts[0:self.B:e].copy_(self.corners)
+        self.counts[0:self.B:e].copy_(self.ccounts)
+
+    def stage_track(self, want_iters=False):
+        prev = [lv[0:self.B] for lv in self.levels]
+        nxt = [lv[1:self.B + 1] for lv in self.levels]
+        out = ops.pyrlk(prev, nxt, self.pts, self.params, counts=self.counts, want_iters=want_iters,
+                        out=(self.next_pts, self.status, self.err))
+        if want_iters:
+            self.iters = out[3]
+
+    def stage_carry(self):
+        for lv in self.levels:
+            lv[0].copy_(lv[self.B])
+
+    def step(self, bgr):
+        """bgr: [B,H,W,3] uint8 CUDA tensor = the B new frames of this step."""
+        self.stage_process(bgr)
+        self.stage_pyramid()
+        self.stage_refresh()
+        self.stage_track()
+        self.stage_carry()
+
+    # -- CUDA graph ------------------------------------------------------------------------------
+    def capture(self, bgr):
+        """Record one step on `bgr` (a persistent input buffer) into a CUDA graph; returns replay()."""
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(bgr)
+        self.graph = g
+        return g.replay
+
+    def results(self):
+        return self.next_pts, self.status, self.err, self.counts
+
+
+class HostFeeder:
+    """Host-buffer front end of PairPipeline: pinned host frames/points in, pinned host tracks out.
+
+    H2D copies run on a dedicated copy stream into one of two device input slots while the previous
+    step computes (double buffering); results return through pinned buffers (also two slots, so the
+    tuple returned for step k is valid until step k+2 is issued)."""
+
+    def __init__(self, pipe):
+        self.pipe = pipe
+        p = pipe
+        self.copy_stream = torch.cuda.Stream(device=p.dev)
+        self.in_frames = [torch.empty((p.B, p.H, p.W, 3), dtype=torch.uint8, device=p.dev) for _ in range(2)]
+        self.in_pts = [torch.empty((p.B, p.N, 2), dtype=torch.float32, device=p.dev) for _ in range(2)]
+        self.out = [(torch.empty((p.B, p.N, 2), dtype=torch.float32).pin_memory(),
+                     torch.empty((p.B, p.N), dtype=torch.uint8).pin_memory(),
+                     torch.empty((p.B, p.N), dtype=torch.float32).pin_memory(),
+                     torch.empty((p.B,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+
+    def run(self, batches):
+        """batches: iterable of (frames [B,H,W,3] uint8, pts [B,N,2] float32) host tensors (pinned for
+        asynchronous copies).  Returns the list of per-step (next_pts, status, err, counts) host tuples."""
+        p = self.pipe
+        compute = torch.cuda.current_stream()
+        h2d = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        d2h = [torch.cuda.Event() for _ in range(2)]
+        outs = []
+        for k, (frames, pts) in enumerate(batches):
+            s = k & 1
+            with torch.cuda.stream(self.copy_stream):
+                if k >= 2:
+                    self.copy_stream.wait_event(done[s])          # slot s is free once step k-2 computed
+                self.in_frames[s].copy_(frames, non_blocking=True)
+                self.in_pts[s].copy_(pts, non_blocking=True)
+                h2d[s].record(self.copy_stream)
+            compute.wait_event(h2d[s])
+            p.set_points(self.in_pts[s])
+            p.counts.fill_(p.N)
+            p.step(self.in_frames[s])
+            done[s].record(compute)
+            if k >= 2:
+                d2h[s].synchronize()                              # host slot s consumed (step k-2 landed)
+            for dst, src in zip(self.out[s], p.results()):
+                dst.copy_(src, non_blocking=True)
+            d2h[s].record(compute)
+            outs.append(self.out[s])
+        for e in d2h:
+            e.synchronize()
+        return outs
