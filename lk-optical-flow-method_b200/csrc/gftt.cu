@@ -5,6 +5,7 @@
 //       (value desc, raster index desc) -> greedy min-distance on a cell grid, in score order
 //                                                                    (oracle lko_gftt_select)
 #include "common.cuh"
+#include <math.h>
 
 namespace {
 
@@ -182,104 +183,139 @@ k_nms_compact(const float *__restrict__ eig, long long erp, long long eip, int H
     }
 }
 
-// sort (bitonic, one CTA per list, keys in global/L2) + greedy min-distance (warp 0), SURVEY A.5 (5)-(7)
+// sort (bitonic, one CTA per list) + min-distance selection, SURVEY A.5 (5)-(7).
+//
+// cv2's greedy pass ("visit candidates in score order; accept unless an already ACCEPTED corner lies
+// within minDistance") is evaluated by a parallel fixed point that yields exactly the same set:
+// candidate i is REJECTED as soon as a higher-ranked neighbour (distance < minDistance) is ACCEPTED, and
+// ACCEPTED once all its higher-ranked neighbours are REJECTED; the strongest candidate has no
+// higher-ranked neighbour, so by induction over the rank every candidate gets the greedy verdict.  All
+// undecided candidates are examined concurrently each round (1024 threads); rounds = longest dependency
+// chain (a handful on images).  Neighbours come from a uniform grid of linked lists (cell side >=
+// minDistance, 3x3 search) held in shared memory; "stop at maxCorners" is a rank-ordered prefix count.
+// (cv2 searches the 3x3 block of its round(minDistance) cells; a corner closer than minDistance is never
+// two such cells away, so "any accepted corner within minDistance" is the same predicate.)
 constexpr int SS_NT = 1024;
+constexpr int SS_SMEM_KEYS = 8192;
+constexpr int SS_MAX_CELLS = 24 * 1024;           // uint32 heads in shared memory (96 KB)
+constexpr unsigned SS_NIL = 0xffffffffu;
 
 __global__ void __launch_bounds__(SS_NT)
 k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__ counts, int cap, int W, int H,
-              int max_corners, double min_distance, int cell, int gw, int gh, uint32_t *__restrict__ grid_all,
-              float *__restrict__ corners, int32_t *__restrict__ out_counts, int max_out)
+              int max_corners, double min_distance, int cs, int gw, int gh, unsigned *__restrict__ gnext_all,
+              unsigned char *__restrict__ gstate_all, float *__restrict__ corners, int32_t *__restrict__ out_counts,
+              int max_out)
 {
-    const int list = blockIdx.x;
-    unsigned long long *keys = keys_all + (long long)list * cap;
+    extern __shared__ __align__(16) unsigned char ss_smem[];
+    __shared__ int s_scan[SS_NT / 32];
+    __shared__ int s_base;
+    const int list = blockIdx.x, tid = threadIdx.x;
+    unsigned long long *gkeys = keys_all + (long long)list * cap;
     int n = counts[list];
     const bool overflow = n > cap;
     if (overflow) n = cap;
     int npad = 32;
     while (npad < n) npad <<= 1;
-    for (int i = n + threadIdx.x; i < npad; i += SS_NT) keys[i] = 0ull;
-    // the cell grid: 4 slots per cell, each 0xffffffff (empty) or (y<<16|x)
-    uint32_t *grid = grid_all + (size_t)list * gw * gh * 4;
-    if (min_distance >= 1)
-        for (int i = threadIdx.x; i < gw * gh * 4; i += SS_NT) grid[i] = 0xffffffffu;
+    const bool in_smem = npad <= SS_SMEM_KEYS;
+    unsigned long long *keys = in_smem ? reinterpret_cast<unsigned long long *>(ss_smem) : gkeys;
+    unsigned *heads = reinterpret_cast<unsigned *>(ss_smem + (size_t)SS_SMEM_KEYS * 8);
+    unsigned *nxt = in_smem ? heads + SS_MAX_CELLS : gnext_all + (size_t)list * cap;
+    volatile unsigned char *state = in_smem ? reinterpret_cast<unsigned char *>(heads + SS_MAX_CELLS + SS_SMEM_KEYS)
+                                            : gstate_all + (size_t)list * cap;
+    if (in_smem)
+        for (int i = tid; i < n; i += SS_NT) keys[i] = gkeys[i];
+    for (int i = n + tid; i < npad; i += SS_NT) keys[i] = 0ull;
     __syncthreads();
     for (int k = 2; k <= npad; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < npad; i += SS_NT) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long a = keys[i], c = keys[ixj];
-                    bool desc = (i & k) == 0;
-                    if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
-                }
+            for (int t = tid; t < (npad >> 1); t += SS_NT) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // lower index of the pair
+                int ixj = i | j;
+                unsigned long long a = keys[i], b = keys[ixj];
+                bool desc = (i & k) == 0;
+                if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
             }
             __syncthreads();
         }
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    float *out = corners + (size_t)list * max_out * 2;
-    int nc = 0;
-    const int limit = (max_corners > 0 && max_corners < max_out) ? max_corners : max_out;
-    bool truncated = false;
-    if (min_distance >= 1) {
-        const double md2 = min_distance * min_distance;
-        bool done = false;
-        for (int base = 0; base < n && !done; base += 32) {
-            int i = base + lane;
-            bool good = i < n;
-            int x = 0, y = 0;
-            if (good) {
-                unsigned idx = (unsigned)(keys[i] & 0xffffffffull);
-                y = idx / W; x = idx - y * W;
-                int xc = x / cell, yc = y / cell;
-                int x1 = max(0, xc - 1), y1 = max(0, yc - 1), x2 = min(gw - 1, xc + 1), y2 = min(gh - 1, yc + 1);
-                for (int yy = y1; yy <= y2 && good; yy++)
-                    for (int xx = x1; xx <= x2 && good; xx++) {
-                        const uint4 sl = *reinterpret_cast<const uint4 *>(grid + (size_t)(yy * gw + xx) * 4);
-                        const uint32_t s[4] = {sl.x, sl.y, sl.z, sl.w};
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (s[q] != 0xffffffffu) {
-                                float dx = (float)(x - (int)(s[q] & 0xffff)), dy = (float)(y - (int)(s[q] >> 16));
-                                if ((double)(dx * dx + dy * dy) < md2) good = false;
-                            }
-                    }
-            }
-            unsigned bal = __ballot_sync(0xffffffffu, good);
-            while (bal) {
-                int leader = __ffs(bal) - 1;
-                int lx = __shfl_sync(0xffffffffu, x, leader), ly = __shfl_sync(0xffffffffu, y, leader);
-                if (lane == leader) {
-                    uint32_t *c = grid + (size_t)((y / cell) * gw + (x / cell)) * 4;
-                    int q = 0;
-                    while (q < 3 && c[q] != 0xffffffffu) q++;
-                    c[q] = ((uint32_t)y << 16) | (uint32_t)x;
-                    if (nc < max_out) { out[2 * nc] = (float)x; out[2 * nc + 1] = (float)y; }
-                    good = false;
-                }
-                nc++;
-                if (nc == limit) { done = true; if (max_corners <= 0 || max_corners > max_out) truncated = true; break; }
-                if (good) {
-                    float dx = (float)(x - lx), dy = (float)(y - ly);
-                    if (abs(x / cell - lx / cell) <= 1 && abs(y / cell - ly / cell) <= 1 && (double)(dx * dx + dy * dy) < md2)
-                        good = false;
-                }
-                bal = __ballot_sync(0xffffffffu, good);
-            }
-            __syncwarp();
-        }
-    } else {
-        int take = n < limit ? n : limit;
-        for (int i = lane; i < take; i += 32) {
-            unsigned idx = (unsigned)(keys[i] & 0xffffffffull);
-            int y = idx / W, x = idx - y * W;
-            out[2 * i] = (float)x; out[2 * i + 1] = (float)y;
-        }
-        nc = take;
-        if (n > limit && (max_corners <= 0 || max_corners > max_out)) truncated = true;
+    // low word of every key: raster index -> (y << 16 | x)
+    unsigned *xy = reinterpret_cast<unsigned *>(keys);           // xy[2*i]
+    for (int i = tid; i < n; i += SS_NT) {
+        unsigned idx = xy[2 * i];
+        unsigned y = idx / (unsigned)W, x = idx - y * (unsigned)W;
+        xy[2 * i] = (y << 16) | x;
+        state[i] = (min_distance >= 1) ? 0 : 1;
     }
-    // negative count = capacity problem (candidate scratch or output rows too small): host raises
-    if (lane == 0) out_counts[list] = (overflow || truncated) ? -1 - nc : nc;
+    if (min_distance >= 1) {
+        for (int i = tid; i < gw * gh; i += SS_NT) heads[i] = SS_NIL;
+        __syncthreads();
+        for (int i = tid; i < n; i += SS_NT) {
+            unsigned v = xy[2 * i];
+            int cell = ((v >> 16) / cs) * gw + (v & 0xffff) / cs;
+            nxt[i] = atomicExch(&heads[cell], (unsigned)i);
+        }
+        __syncthreads();
+        const float md2 = (float)(min_distance * min_distance);     // integer coordinates: d2 is exact
+        const bool md2_exact = (double)md2 == min_distance * min_distance;
+        for (;;) {
+            int pending = 0;
+            for (int i = tid; i < n; i += SS_NT) {
+                if (state[i]) continue;
+                unsigned v = xy[2 * i];
+                int x = v & 0xffff, y = v >> 16;
+                int cx = x / cs, cy = y / cs;
+                int verdict = 1;
+                for (int yy = max(0, cy - 1); yy <= min(gh - 1, cy + 1) && verdict != 2; yy++)
+                    for (int xx = max(0, cx - 1); xx <= min(gw - 1, cx + 1) && verdict != 2; xx++)
+                        for (unsigned j = heads[yy * gw + xx]; j != SS_NIL; j = nxt[j]) {
+                            if ((int)j >= i) continue;
+                            unsigned u = xy[2 * j];
+                            float dx = (float)(x - (int)(u & 0xffff)), dy = (float)(y - (int)(u >> 16));
+                            float d2 = dx * dx + dy * dy;
+                            bool close = md2_exact ? (d2 < md2) : ((double)d2 < min_distance * min_distance);
+                            if (close) {
+                                unsigned sj = state[j];
+                                if (sj == 1) { verdict = 2; break; }
+                                if (sj == 0) verdict = 0;
+                            }
+                        }
+                if (verdict) state[i] = (unsigned char)verdict; else pending = 1;
+            }
+            if (!__syncthreads_or(pending)) break;
+        }
+    }
+    __syncthreads();
+    // rank-ordered compaction of the accepted candidates, cut at `limit`
+    float *out = corners + (size_t)list * max_out * 2;
+    const int limit = (max_corners > 0 && max_corners < max_out) ? max_corners : max_out;
+    const bool may_truncate = max_corners <= 0 || max_corners > max_out;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += SS_NT) {
+        int i = base + tid;
+        int acc = (i < n && state[i] == 1) ? 1 : 0;
+        unsigned bal = __ballot_sync(0xffffffffu, acc);
+        int lane = tid & 31, wid = tid >> 5;
+        if (lane == 0) s_scan[wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int w = 0; w < SS_NT / 32; w++) { int c = s_scan[w]; if (w < wid) woff += c; total += c; }
+        int pos = s_base + woff + __popc(bal & ((1u << lane) - 1));
+        if (acc && pos < limit) {
+            unsigned v = xy[2 * i];
+            out[2 * pos] = (float)(v & 0xffff); out[2 * pos + 1] = (float)(v >> 16);
+        }
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
+        if (s_base >= limit && !may_truncate) break;
+    }
+    if (tid == 0) {
+        int total = s_base;
+        int nc = total < limit ? total : limit;
+        bool truncated = may_truncate && total > limit;
+        // negative count = capacity problem (candidate scratch or output rows too small): host raises
+        out_counts[list] = (overflow || truncated) ? -1 - nc : nc;
+    }
 }
 
 }  // namespace
@@ -331,16 +367,23 @@ LKF_EXPORT int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf
     long long cap_ll = P / 4 + 4096;
     int cap = 32;
     while (cap < cap_ll) cap <<= 1;
-    int cell = 1, gw = 1, gh = 1;
+    // neighbour grid: cell side >= minDistance (3x3 search suffices), grown until the heads fit in smem
+    int cs = 1, gw = 1, gh = 1;
     if (p->min_distance >= 1) {
-        cell = (int)nearbyint(p->min_distance);
-        gw = (W + cell - 1) / cell; gh = (H + cell - 1) / cell;
+        cs = (int)ceil(p->min_distance);
+        for (;;) {
+            gw = (W + cs - 1) / cs; gh = (H + cs - 1) / cs;
+            if ((long long)gw * gh <= SS_MAX_CELLS) break;
+            cs++;
+        }
     }
-    void *keys, *cnt, *grid;
+    if (W > 65535 || H > 65535) return LKF_ERR_UNSUPPORTED;
+    const size_t ss_smem = (size_t)SS_SMEM_KEYS * 8 + (size_t)SS_MAX_CELLS * 4 + (size_t)SS_SMEM_KEYS * 4 + SS_SMEM_KEYS;
+    void *keys, *cnt, *gaux;
     int rc;
     if ((rc = lkf_scratch(ctx, 0, (size_t)lists * cap * 8, &keys)) != LKF_OK) return rc;
     if ((rc = lkf_scratch(ctx, 1, (size_t)lists * 2 * sizeof(int), &cnt)) != LKF_OK) return rc;
-    if ((rc = lkf_scratch(ctx, 2, (size_t)lists * gw * gh * 16, &grid)) != LKF_OK) return rc;
+    if ((rc = lkf_scratch(ctx, 2, (size_t)lists * cap * 5, &gaux)) != LKF_OK) return rc;     // next (u32) + state (u8), large lists only
     cudaStream_t s = (cudaStream_t)stream;
     unsigned *maxkey = (unsigned *)cnt;
     int *ccount = (int *)cnt + lists;
@@ -353,8 +396,14 @@ LKF_EXPORT int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf
     k_nms_compact<<<g2, 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, maxkey,
                                      p->quality_level, (unsigned long long *)keys, ccount, cap);
     LKF_LAUNCH_CHECK(ctx);
-    k_sort_select<<<lists, SS_NT, 0, s>>>((unsigned long long *)keys, ccount, cap, W, H, p->max_corners, p->min_distance, cell, gw,
-                                         gh, (uint32_t *)grid, corners, counts, max_out);
+    static bool ss_attr = false;
+    if (!ss_attr) {
+        LKF_CUDA(cudaFuncSetAttribute(k_sort_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_smem));
+        ss_attr = true;
+    }
+    k_sort_select<<<lists, SS_NT, ss_smem, s>>>((unsigned long long *)keys, ccount, cap, W, H, p->max_corners, p->min_distance, cs, gw,
+                                               gh, (unsigned *)gaux, (unsigned char *)gaux + (size_t)lists * cap * 4, corners, counts,
+                                               max_out);
     LKF_LAUNCH_CHECK(ctx);
     return LKF_OK;
 }

@@ -250,6 +250,307 @@ k_lk_track(LKLevels lv, int n_levels, int w, int h, int max_count, double eps2, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Specialised tracker for the window sizes the configs name (15x15, 21x21, 31x31): everything is a
+// compile-time constant, the template patch lives in REGISTERS, each lane owns horizontal runs of
+// RUN window pixels (2*(RUN+1) byte loads per run instead of 4*RUN), and `next` is sampled from a
+// per-warp shared-memory tile (window + MARGIN on every side, loaded once per level with aligned
+// 32-bit loads and re-centred only if the iterate walks out of it).
+// ---------------------------------------------------------------------------------------------
+constexpr int LKT_WARPS = 4;     // small CTAs: a CTA retires when its slowest feature converges
+
+template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_>
+struct LKT {
+    static constexpr int AREA = WW * WH;
+    static constexpr int RPR = WW / RUN;                 // runs per window row
+    static constexpr int NRUNS = RPR * WH;
+    static constexpr int RPL = (NRUNS + 31) / 32;        // runs per lane
+    static constexpr int RW = WW + 3, RH = WH + 3, RWP = (RW + 3) & ~3;
+    static constexpr int DW = WW + 1, DH = WH + 1, DWP = DWP_;      // DWP: der pitch (words), chosen bank-conflict-poor
+    static constexpr int TWC = TWC_;                                  // tile pitch (bytes), multiple of 4
+    static constexpr int TH = WH + 1 + 2 * MARGIN;
+    static constexpr int DER_BYTES = (DWP * DH * 4 + 15) & ~15, TILE_BYTES = (TWC * TH + 15) & ~15;
+    static constexpr int RAW_BYTES = (RWP * RH + 15) & ~15;
+    static constexpr int PER_WARP = DER_BYTES + TILE_BYTES + RAW_BYTES;
+    static_assert(WW % RUN == 0, "RUN must divide the window width");
+    static_assert(AREA <= 2048, "int32 lane partials");
+    static_assert(TWC % 4 == 0 && TWC >= WW + 1 + 2 * MARGIN + 3, "tile pitch");
+    static_assert(DWP >= DW, "der pitch");
+};
+
+// tile origin: window + MARGIN, x aligned down to 4; slid back inside the level when the window itself is inside
+// (keeps the aligned 32-bit fast path for features near the border)
+template <class T>
+__device__ __forceinline__ void place_tile(int ix, int iy, int W, int H, int &tx0, int &ty0)
+{
+    constexpr int WW1 = T::DW, WH1 = T::DH;       // footprint of the window samples
+    tx0 = ((ix - (T::TWC - WW1 - 3) / 2) >> 2) << 2;
+    ty0 = iy - (T::TH - WH1) / 2;
+    if (ix >= 0 && ix + WW1 <= W && W >= T::TWC) {
+        const int c = min(max(tx0, 0), ((W - T::TWC) >> 2) << 2);
+        if (ix + WW1 <= c + T::TWC) tx0 = c;           // (alignment can cost up to 3 columns at the right edge)
+    }
+    if (iy >= 0 && iy + WH1 <= H && H >= T::TH) ty0 = min(max(ty0, 0), H - T::TH);
+}
+
+template <class T>
+__device__ __forceinline__ void load_j_tile(const uint8_t *__restrict__ J, long long rp, int W, int H, bool al4,
+                                            int tx0, int ty0, unsigned char *tile, int lane)
+{
+    constexpr int WPR = T::TWC / 4;
+    const bool inside = tx0 >= 0 && ty0 >= 0 && tx0 + T::TWC <= W && ty0 + T::TH <= H;
+    if (inside && al4) {
+        const uint8_t *base = J + (long long)ty0 * rp + tx0;
+#pragma unroll 4
+        for (int i = lane; i < WPR * T::TH; i += 32) {
+            int r = i / WPR, k = i - r * WPR;
+            reinterpret_cast<uint32_t *>(tile)[i] = __ldg(reinterpret_cast<const uint32_t *>(base + (long long)r * rp) + k);
+        }
+    } else {
+        for (int i = lane; i < T::TWC * T::TH; i += 32) {
+            int r = i / T::TWC, c = i - r * T::TWC;
+            tile[i] = J[(long long)reflect101(ty0 + r, H) * rp + reflect101(tx0 + c, W)];
+        }
+    }
+}
+
+template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, int MINB>
+__global__ void __launch_bounds__(LKT_WARPS * 32, MINB)
+k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, double min_eig_thr,
+             const float *__restrict__ prev_pts, const int *__restrict__ counts, int max_pts,
+             float *__restrict__ next_pts, uint8_t *__restrict__ status, float *__restrict__ err,
+             int *__restrict__ iters_out, unsigned al4_mask)
+{
+    using T = LKT<WW, WH, RUN, MARGIN, DWP_, TWC_>;
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pt = blockIdx.x * LKT_WARPS + warp, b = blockIdx.y;
+    const int n = counts ? counts[b] : max_pts;
+    if (pt >= n || pt >= max_pts) return;
+
+    unsigned char *uni = smem_all + (size_t)warp * T::PER_WARP;
+    short2 *der = reinterpret_cast<short2 *>(uni);          // Scharr on the sample grid (setup phase)
+    unsigned char *tile = uni + T::DER_BYTES;                // `next` tile (prefetched at level entry)
+    unsigned char *raw = tile + T::TILE_BYTES;
+
+    // this lane's runs: (row, first column) -- compile-time count, runtime validity
+    int run_y[T::RPL], run_x[T::RPL];
+    bool run_ok[T::RPL];
+#pragma unroll
+    for (int k = 0; k < T::RPL; k++) {
+        int r = lane + 32 * k;
+        run_ok[k] = r < T::NRUNS;
+        if (!run_ok[k]) r = 0;
+        run_y[k] = r / T::RPR;
+        run_x[k] = (r - run_y[k] * T::RPR) * RUN;
+    }
+
+    const long long pidx = (long long)b * max_pts + pt;
+    const float ppx = prev_pts[2 * pidx], ppy = prev_pts[2 * pidx + 1];
+    const float hx = (WW - 1) * 0.5f, hy = (WH - 1) * 0.5f;
+    float npx = 0.f, npy = 0.f;
+    if (flags & LKF_OPTFLOW_USE_INITIAL_FLOW) { npx = next_pts[2 * pidx]; npy = next_pts[2 * pidx + 1]; }
+    bool st = true;
+    float ev = 0.f;
+    int iters = 0;
+    const float FLT_SCALE = 1.f / (1 << 20);
+
+    for (int l = n_levels - 1; l >= 0; --l) {
+        const int W = lv.W[l], H = lv.H[l];
+        const uint8_t *I = lv.prev[l] + (long long)b * lv.pip[l];
+        const uint8_t *J = lv.next[l] + (long long)b * lv.nip[l];
+        const long long irp = lv.prp[l], jrp = lv.nrp[l];
+        const bool jal4 = (al4_mask >> l) & 1u;
+        const float sc = 1.f / (float)(1 << l);
+        float px = __fmul_rn(ppx, sc), py = __fmul_rn(ppy, sc);
+        float nx, ny;
+        if (l == n_levels - 1) {
+            if (flags & LKF_OPTFLOW_USE_INITIAL_FLOW) { nx = __fmul_rn(npx, sc); ny = __fmul_rn(npy, sc); }
+            else { nx = px; ny = py; }
+        } else { nx = __fmul_rn(npx, 2.f); ny = __fmul_rn(npy, 2.f); }
+        npx = nx; npy = ny;
+        px = __fsub_rn(px, hx); py = __fsub_rn(py, hy);
+        const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+        if (out_of_level(px, py, ipx, ipy, WW, WH, W, H)) {
+            if (l == 0) { st = false; ev = 0.f; }
+            continue;
+        }
+        int w00, w01, w10, w11;
+        weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+
+        // prefetch the `next` tile around the entry estimate (independent of the template set-up below)
+        int tx0, ty0;
+        __syncwarp();
+        {
+            const float fx = __fsub_rn(nx, hx), fy = __fsub_rn(ny, hy);
+            place_tile<T>(__float2int_rd(fx), __float2int_rd(fy), W, H, tx0, ty0);
+            load_j_tile<T>(J, jrp, W, H, jal4, tx0, ty0, tile, lane);
+        }
+        // 1. raw (WW+3)x(WH+3) neighbourhood of prev, mirrored
+        {
+            const bool inside = ipx >= 1 && ipy >= 1 && ipx + WW + 1 < W && ipy + WH + 1 < H;
+            if (inside) {
+                const uint8_t *base = I + (long long)(ipy - 1) * irp + (ipx - 1);
+#pragma unroll 6
+                for (int idx = lane; idx < T::RW * T::RH; idx += 32) {
+                    int j = idx / T::RW, i = idx - j * T::RW;
+                    raw[j * T::RWP + i] = __ldg(base + (long long)j * irp + i);
+                }
+            } else {
+                for (int idx = lane; idx < T::RW * T::RH; idx += 32) {
+                    int j = idx / T::RW, i = idx - j * T::RW;
+                    raw[j * T::RWP + i] = I[(long long)reflect101(ipy - 1 + j, H) * irp + reflect101(ipx - 1 + i, W)];
+                }
+            }
+        }
+        __syncwarp();
+        // 2. Scharr on the (WW+1)x(WH+1) sample grid, zero outside the level
+        {
+            const bool inside = ipx >= 0 && ipy >= 0 && ipx + WW < W && ipy + WH < H;
+#pragma unroll 4
+            for (int idx = lane; idx < T::DW * T::DH; idx += 32) {
+                int j = idx / T::DW, i = idx - j * T::DW;
+                const unsigned char *r0 = raw + j * T::RWP + i, *r1 = r0 + T::RWP, *r2 = r1 + T::RWP;
+                int a0 = r0[0], a1 = r0[1], a2 = r0[2], b0 = r1[0], b2 = r1[2], c0 = r2[0], c1 = r2[1], c2 = r2[2];
+                int ix = 3 * (a2 - a0 + c2 - c0) + 10 * (b2 - b0);
+                int iy = 3 * (c0 - a0 + c2 - a2) + 10 * (c1 - a1);
+                if (!inside) {
+                    int qx = ipx + i, qy = ipy + j;
+                    if (qx < 0 || qx >= W || qy < 0 || qy >= H) { ix = 0; iy = 0; }
+                }
+                der[j * T::DWP + i] = make_short2((short)ix, (short)iy);
+            }
+        }
+        __syncwarp();
+        // 3. template patch (registers) + structure tensor
+        unsigned pI[T::RPL][(RUN + 1) / 2];      // I*32 packed two per register
+        unsigned pD[T::RPL][RUN];                // (Ix & 0xffff) | Iy << 16
+        int a11 = 0, a12 = 0, a22 = 0;
+#pragma unroll
+        for (int k = 0; k < T::RPL; k++) {
+            const unsigned char *r0 = raw + (run_y[k] + 1) * T::RWP + run_x[k] + 1, *r1 = r0 + T::RWP;
+            const short2 *d0 = der + run_y[k] * T::DWP + run_x[k], *d1 = d0 + T::DWP;
+            int i00 = r0[0], i10 = r1[0];
+            short2 e00 = d0[0], e10 = d1[0];
+#pragma unroll
+            for (int t = 0; t < RUN; t++) {
+                int i01 = r0[t + 1], i11 = r1[t + 1];
+                short2 e01 = d0[t + 1], e11 = d1[t + 1];
+                int iv = descale(i00 * w00 + i01 * w01 + i10 * w10 + i11 * w11, 9);
+                int ixv = descale(e00.x * w00 + e01.x * w01 + e10.x * w10 + e11.x * w11, 14);
+                int iyv = descale(e00.y * w00 + e01.y * w01 + e10.y * w10 + e11.y * w11, 14);
+                if (!run_ok[k]) { iv = 0; ixv = 0; iyv = 0; }
+                if (t & 1) pI[k][t / 2] |= (unsigned)iv << 16; else pI[k][t / 2] = (unsigned)iv;
+                pD[k][t] = ((unsigned)ixv & 0xffffu) | ((unsigned)iyv << 16);
+                a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv;
+                i00 = i01; i10 = i11; e00 = e01; e10 = e11;
+            }
+        }
+        const float A11 = __fmul_rn((float)warp_sum(a11), FLT_SCALE);
+        const float A12 = __fmul_rn((float)warp_sum(a12), FLT_SCALE);
+        const float A22 = __fmul_rn((float)warp_sum(a22), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dd = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * WW * WH));
+        if (flags & LKF_OPTFLOW_LK_GET_MIN_EIGENVALS) ev = minEig;
+        if ((double)minEig < min_eig_thr || D < 1.1920929e-07f) {
+            if (l == 0) st = false;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        nx = __fsub_rn(nx, hx); ny = __fsub_rn(ny, hy);
+        float pdx = 0.f, pdy = 0.f;
+
+        // samples `next` at (ix,iy) through the smem tile; f(k, t, value) for every owned window pixel
+        auto sweep = [&](int ix, int iy, auto f) {
+            int ox = ix - tx0, oy = iy - ty0;
+            if (ox < 0 || oy < 0 || ox + WW + 1 > T::TWC || oy + WH + 1 > T::TH) {
+                __syncwarp();
+                place_tile<T>(ix, iy, W, H, tx0, ty0);
+                load_j_tile<T>(J, jrp, W, H, jal4, tx0, ty0, tile, lane);
+                __syncwarp();
+                ox = ix - tx0; oy = iy - ty0;
+            }
+#pragma unroll
+            for (int k = 0; k < T::RPL; k++) {
+                const unsigned char *r0 = tile + (oy + run_y[k]) * T::TWC + ox + run_x[k], *r1 = r0 + T::TWC;
+                int j00 = r0[0], j10 = r1[0];
+#pragma unroll
+                for (int t = 0; t < RUN; t++) {
+                    int j01 = r0[t + 1], j11 = r1[t + 1];
+                    int v = descale(j00 * w00 + j01 * w01 + j10 * w10 + j11 * w11, 9);
+                    int iv = (t & 1) ? (int)(pI[k][t / 2] >> 16) : (int)(pI[k][t / 2] & 0xffffu);
+                    f(k, t, run_ok[k] ? v - iv : 0);
+                    j00 = j01; j10 = j11;
+                }
+            }
+        };
+
+        for (int j = 0; j < max_count; j++) {
+            const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+            if (out_of_level(nx, ny, inx, iny, WW, WH, W, H)) {
+                if (l == 0) st = false;
+                break;
+            }
+            weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+            int b1 = 0, b2 = 0;
+            sweep(inx, iny, [&](int k, int t, int diff) { b1 += diff * (int)(short)(pD[k][t] & 0xffffu); b2 += diff * ((int)pD[k][t] >> 16); });
+            iters++;
+            const float fb1 = __fmul_rn((float)warp_sum(b1), FLT_SCALE);
+            const float fb2 = __fmul_rn((float)warp_sum(b2), FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            npx = __fadd_rn(nx, hx); npy = __fadd_rn(ny, hy);
+            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2) break;
+            if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+                npx = __fsub_rn(npx, __fmul_rn(dx, 0.5f));
+                npy = __fsub_rn(npy, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (st && l == 0 && !(flags & LKF_OPTFLOW_LK_GET_MIN_EIGENVALS)) {
+            const float ex = __fsub_rn(npx, hx), ey = __fsub_rn(npy, hy);
+            const int iex = __float2int_rd(ex), iey = __float2int_rd(ey);
+            if (out_of_level(ex, ey, iex, iey, WW, WH, W, H)) { st = false; continue; }
+            weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
+            int se = 0;
+            sweep(iex, iey, [&](int, int, int diff) { se += diff < 0 ? -diff : diff; });
+            ev = __fdiv_rn((float)warp_sum(se), (float)(32 * WW * WH));
+        }
+    }
+    if (lane == 0) {
+        next_pts[2 * pidx] = npx;
+        next_pts[2 * pidx + 1] = npy;
+        status[pidx] = st ? 1 : 0;
+        err[pidx] = st ? ev : 0.f;
+        if (iters_out) iters_out[pidx] = iters;
+    }
+}
+
+template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, int MINB>
+int launch_lk_t(const LKLevels &lv, int n_levels, int max_count, double eps, const lkf_lk_params *p, const float *prev_pts,
+                const int32_t *pt_counts, int max_pts, float *next_pts, uint8_t *status, float *err, int32_t *iters,
+                unsigned al4_mask, int B, cudaStream_t s)
+{
+    using T = LKT<WW, WH, RUN, MARGIN, DWP_, TWC_>;
+    constexpr size_t smem = (size_t)T::PER_WARP * LKT_WARPS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        LKF_CUDA(cudaFuncSetAttribute(k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LKF_CUDA(cudaFuncSetAttribute(k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    dim3 grid((max_pts + LKT_WARPS - 1) / LKT_WARPS, B);
+    k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB><<<grid, LKT_WARPS * 32, smem, s>>>(
+        lv, n_levels, max_count, eps, p->flags, p->min_eig_threshold, prev_pts, pt_counts, max_pts, next_pts, status, err, iters,
+        al4_mask);
+    return LKF_OK;
+}
+
 size_t lk_per_warp_bytes(int w, int h)
 {
     size_t area = (size_t)w * h;
@@ -296,6 +597,18 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     const int area = p->win_w * p->win_h;
     dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, B);
     cudaStream_t s = (cudaStream_t)stream;
+    unsigned al4_mask = 0;
+    for (int l = 0; l < n_levels; l++)
+        if (aligned_to(&next_pyr[l], 4)) al4_mask |= 1u << l;
+    int rc = 1;
+    if (p->win_w == 21 && p->win_h == 21)
+        rc = launch_lk_t<21, 21, 7, 6, 22, 52, 5>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, B, s);
+    else if (p->win_w == 15 && p->win_h == 15)
+        rc = launch_lk_t<15, 15, 5, 6, 17, 36, 6>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, B, s);
+    else if (p->win_w == 31 && p->win_h == 31)
+        rc = launch_lk_t<31, 31, 31, 6, 33, 52, 3>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, B, s);
+    if (rc < 0) return rc;
+    if (rc == LKF_OK) { LKF_LAUNCH_CHECK(ctx); return LKF_OK; }
     if (area <= 2048) {      // int32 lane partials cannot overflow (<= 64 px/lane * 8160*4080)
         if (smem > 48 * 1024) LKF_CUDA(cudaFuncSetAttribute(k_lk_track<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_lk_track<int><<<grid, LK_WARPS * 32, smem, s>>>(lv, n_levels, p->win_w, p->win_h, max_count, eps, p->flags,
