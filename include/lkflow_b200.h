@@ -118,6 +118,62 @@ int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *params, const lkf_image
                     const lkf_image *mask_u8, int n_masks, float *corners, int32_t *counts,
                     int max_out, lkf_stream stream);
 
+/* ---- a5+a6 fused for a batch: cv.goodFeaturesToTrack(img, mask=m, **feature_params) for every image and each of
+ *      its n_masks masks (the scripts call it 4x per refresh on the same image, VP.py:500-507, 702-711); the eig map
+ *      lives in the workspace.  image_enable (nullable, device int32[B]): images with 0 are skipped on the device. */
+int lkf_gftt_detect(lkf_ctx *ctx, const lkf_gftt_params *params, const lkf_image *src_u8, const lkf_image *mask_u8,
+                    int n_masks, const int32_t *image_enable, float *corners, int32_t *counts, int max_out,
+                    lkf_stream stream);
+
+/* ---- next row (8f.1): imutils.resize(frame, width=860) = cv2.resize(.., INTER_AREA), non-integer down-scale
+ *      (VP.py:433,531).  Tables (host-built, device-resident): destination index d uses entries
+ *      [ofs[d], ofs[d+1]) of (src index, alpha) -- cv2's computeResizeAreaTab. */
+int lkf_resize_area_u8(const lkf_image *src, const lkf_image *dst, const int32_t *xofs, const int32_t *xsi,
+                       const float *xalpha, const int32_t *yofs, const int32_t *ysi, const float *yalpha,
+                       lkf_stream stream);
+
+/* ---- a8-a12: tracks -> flow lines -> cross points -> vanishing point (one frame of every clip per call).
+ *      Replaces the Python glue of VP.py:326-349 (checkInside), 276-283 (FlowLine), 565-574 (acceptance),
+ *      296-324 + 581-595 (cross points), 157-194 + 596-653 (VP state machine, CSV rows), 700 (refresh test).
+ *      Host-computed thresholds are passed as the doubles Python would compute (e.g. TP_NUM*TP_UPDATE_RATE). */
+#define LKF_VP_RING 32
+typedef struct lkf_vp_params {
+    double cp_gate_x, cp_gate_y;       /* WID*CP_THOLD, Hei*CP_THOLD            (VP.py:192-194)      */
+    double min_ang_dif;                /* MIN_ANG_DIF = 25                      (VP.py:586)          */
+    double max_cp_std;                 /* MAX_CP_STD = 1.0                      (VP.py:617-618)      */
+    double vp_update_rate;             /* VP_UPDATE_RATE = 0.5                  (VP.py:181-182)      */
+    double fl_update_rate;             /* FL_UPDATE_RATE = 0.05                 (VP.py:571)          */
+    double min_fl_len;                 /* MIN_FL_LEN = 1.0 (LK_Final.py: 1.5)   (VP.py:570)          */
+    double tp_refresh_below;           /* TP_NUM*TP_UPDATE_RATE                 (VP.py:700)          */
+    float start_x_sep;                 /* float32(WID*0.05); < 0 disables (LK_Final.py has no such filter, VP.py:588) */
+    int32_t vp_ref_num;                /* VP_REF_NUM = 10 (LK_Final.py: 15), <= LKF_VP_RING          */
+    int32_t hide_vp_thold;             /* HIDE_VP_THOLD = 50                    (VP.py:644)          */
+    int32_t reset_avg_on_hide;         /* 1: VP.py:647, 0: LK_Final.py                               */
+    int32_t tp_update_time;            /* TP_UPDATE_TIME = 10                   (VP.py:700)          */
+    int32_t reserved;
+} lkf_vp_params;
+
+typedef struct lkf_vp_state {          /* one per clip, device resident, zero-initialised except avg_len */
+    double vp_x, vp_y;
+    double ring_x[LKF_VP_RING], ring_y[LKF_VP_RING];   /* recent cross points (last LKF_VP_RING) */
+    double avg_len[2];                 /* per-group flow-length EMA, starts at MIN_FL_LEN            */
+    int32_t ring_alias[LKF_VP_RING];   /* 1: this entry IS the VP object (init aliasing) */
+    int32_t vp_init, ring_count, ring_head, vp_ult, tp_ult, n_rows, row_overflow, refresh;
+    int64_t n_lines, n_cps;
+} lkf_vp_state;
+
+/* p0/p1: [n_clips*2][max_pts_per_group][2] float32 (group g of clip b at list 2b+g), status likewise u8,
+ * counts [n_clips*2] int32 (in: tracked points per group; out: survivors, which p0 now holds = `p0s[n] = good_new`).
+ * rows: [n_clips][row_capacity][2] float64, appended at states[b].n_rows.  clip_enable (nullable): skip clip b if 0. */
+int lkf_vp_frame(const lkf_vp_params *params, lkf_vp_state *states, int n_clips, float *p0, const float *p1,
+                 const uint8_t *status, int32_t *counts, int max_pts_per_group, const lkf_image *roi_mask,
+                 double *rows, int row_capacity, int32_t *refresh_out /* nullable: [n_clips] copy of state.refresh */,
+                 const int32_t *clip_enable, lkf_stream stream);
+/* REPlace refresh (VP.py:700-718) from a 4-mask corner detection: lists 4b+0,1 -> group 0, 4b+2,3 -> group 1,
+ * applied where states[b].refresh is set (or everywhere if force) and both new groups are non-empty. */
+int lkf_vp_apply_refresh(lkf_vp_state *states, int n_clips, const float *corners, const int32_t *corner_counts,
+                         int max_out, float *p0, int32_t *counts, int max_pts_per_group, int force, lkf_stream stream);
+
 /* ---- measurement helper (bench.py): FFMA-rate probe; executes blocks*256*iters*16 flops ------- */
 int lkf_probe_fp32_fma(int blocks, int iters, float *out, lkf_stream stream);
 

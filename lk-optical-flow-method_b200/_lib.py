@@ -38,13 +38,27 @@ class LkfGfttParams(ctypes.Structure):
                 ("quality_level", ctypes.c_double), ("min_distance", ctypes.c_double)]
 
 
+LKF_VP_RING = 32
+
+
 class LkfVpParams(ctypes.Structure):
-    _fields_ = [("wid", ctypes.c_double), ("hei", ctypes.c_double), ("min_ang_dif", ctypes.c_double),
-                ("start_x_sep", ctypes.c_double), ("cp_thold", ctypes.c_double),
+    _fields_ = [("cp_gate_x", ctypes.c_double), ("cp_gate_y", ctypes.c_double), ("min_ang_dif", ctypes.c_double),
                 ("max_cp_std", ctypes.c_double), ("vp_update_rate", ctypes.c_double),
                 ("fl_update_rate", ctypes.c_double), ("min_fl_len", ctypes.c_double),
+                ("tp_refresh_below", ctypes.c_double), ("start_x_sep", ctypes.c_float),
                 ("vp_ref_num", ctypes.c_int32), ("hide_vp_thold", ctypes.c_int32),
-                ("reset_avg_len_on_hide", ctypes.c_int32), ("use_start_x_filter", ctypes.c_int32)]
+                ("reset_avg_on_hide", ctypes.c_int32), ("tp_update_time", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
+class LkfVpState(ctypes.Structure):
+    _fields_ = [("vp_x", ctypes.c_double), ("vp_y", ctypes.c_double),
+                ("ring_x", ctypes.c_double * LKF_VP_RING), ("ring_y", ctypes.c_double * LKF_VP_RING),
+                ("avg_len", ctypes.c_double * 2), ("ring_alias", ctypes.c_int32 * LKF_VP_RING),
+                ("vp_init", ctypes.c_int32), ("ring_count", ctypes.c_int32), ("ring_head", ctypes.c_int32),
+                ("vp_ult", ctypes.c_int32), ("tp_ult", ctypes.c_int32), ("n_rows", ctypes.c_int32),
+                ("row_overflow", ctypes.c_int32), ("refresh", ctypes.c_int32),
+                ("n_lines", ctypes.c_int64), ("n_cps", ctypes.c_int64)]
 
 
 _P = ctypes.POINTER
@@ -69,6 +83,10 @@ SIGNATURES = {
                               _vp, _vp, _vp, _vp, _vp]),
     "lkf_corner_min_eigen_f32": (_i, [_P(LkfImage), _P(LkfImage), _i, _i, _vp]),
     "lkf_probe_fp32_fma": (_i, [_i, _i, _vp, _vp]),
+    "lkf_gftt_detect": (_i, [_vp, _P(LkfGfttParams), _P(LkfImage), _P(LkfImage), _i, _vp, _vp, _vp, _i, _vp]),
+    "lkf_resize_area_u8": (_i, [_P(LkfImage), _P(LkfImage), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lkf_vp_frame": (_i, [_P(LkfVpParams), _vp, _i, _vp, _vp, _vp, _vp, _i, _P(LkfImage), _vp, _i, _vp, _vp, _vp]),
+    "lkf_vp_apply_refresh": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "lkf_gftt_select": (_i, [_vp, _P(LkfGfttParams), _P(LkfImage), _P(LkfImage), _i, _vp, _vp, _i, _vp]),
 }
 

@@ -18,9 +18,10 @@ constexpr int ME_W = 64, ME_H = 16, ME_NT = 256;
 
 __global__ void __launch_bounds__(ME_NT)
 k_min_eigen(const uint8_t *__restrict__ src, long long rp, long long ip, int H, int W, float *__restrict__ dst,
-            long long drp, long long dip, int bs, int tail_cols, float s, float s2)
+            long long drp, long long dip, int bs, int tail_cols, float s, float s2, const int32_t *__restrict__ enable)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    if (enable && !enable[blockIdx.z]) return;
     const int r0 = bs / 2;                        // window = [-r0, bs-1-r0]
     const int pw = ME_W + bs - 1, ph = ME_H + bs - 1;     // product tile
     const int uw = pw + 2, uh = ph + 2;                   // u8 tile
@@ -112,9 +113,10 @@ struct MaskSet {
 
 __global__ void __launch_bounds__(256)
 k_masked_max(const float *__restrict__ eig, long long erp, long long eip, int H, int W, MaskSet ms, int n_masks,
-             unsigned *__restrict__ maxkey)
+             unsigned *__restrict__ maxkey, const int32_t *__restrict__ enable)
 {
     const int b = blockIdx.y;
+    if (enable && !enable[b]) return;
     const unsigned char *e = reinterpret_cast<const unsigned char *>(eig) + (long long)b * eip;
     unsigned best[MAXM];
 #pragma unroll
@@ -143,9 +145,10 @@ k_masked_max(const float *__restrict__ eig, long long erp, long long eip, int H,
 __global__ void __launch_bounds__(256)
 k_nms_compact(const float *__restrict__ eig, long long erp, long long eip, int H, int W, MaskSet ms, int n_masks,
               const unsigned *__restrict__ maxkey, double quality, unsigned long long *__restrict__ keys,
-              int *__restrict__ counts, int cap)
+              int *__restrict__ counts, int cap, const int32_t *__restrict__ enable)
 {
     const int b = blockIdx.z;
+    if (enable && !enable[b]) return;
     const int x = 1 + blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = 1 + blockIdx.y * 8 + (threadIdx.x >> 5);
     const unsigned char *e = reinterpret_cast<const unsigned char *>(eig) + (long long)b * eip;
@@ -204,12 +207,13 @@ __global__ void __launch_bounds__(SS_NT)
 k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__ counts, int cap, int W, int H,
               int max_corners, double min_distance, int cs, int gw, int gh, unsigned *__restrict__ gnext_all,
               unsigned char *__restrict__ gstate_all, float *__restrict__ corners, int32_t *__restrict__ out_counts,
-              int max_out)
+              int max_out, const int32_t *__restrict__ enable, int n_masks)
 {
     extern __shared__ __align__(16) unsigned char ss_smem[];
     __shared__ int s_scan[SS_NT / 32];
     __shared__ int s_base;
     const int list = blockIdx.x, tid = threadIdx.x;
+    if (enable && !enable[list / n_masks]) return;
     unsigned long long *gkeys = keys_all + (long long)list * cap;
     int n = counts[list];
     const bool overflow = n > cap;
@@ -320,8 +324,8 @@ k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__
 
 }  // namespace
 
-LKF_EXPORT int lkf_corner_min_eigen_f32(const lkf_image *src, const lkf_image *eig, int block_size, int dy_tail_cols,
-                                        lkf_stream stream)
+static int min_eigen_impl(const lkf_image *src, const lkf_image *eig, int block_size, int dy_tail_cols, const int32_t *enable,
+                          lkf_stream stream)
 {
     if (!img_ok(src, 1, 1) || !img_ok(eig, 1, 4) || src->batch != eig->batch || src->height != eig->height ||
         src->width != eig->width || !aligned_to(eig, 4))
@@ -338,13 +342,19 @@ LKF_EXPORT int lkf_corner_min_eigen_f32(const lkf_image *src, const lkf_image *e
     dim3 grid((W + ME_W - 1) / ME_W, (H + ME_H - 1) / ME_H, src->batch);
     k_min_eigen<<<grid, ME_NT, smem, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch, H, W,
                                                             (float *)eig->data, eig->row_pitch, eig->image_pitch, bs,
-                                                            dy_tail_cols, s, s2);
+                                                            dy_tail_cols, s, s2, enable);
     LKF_LAUNCH_CHECK(nullptr);
     return LKF_OK;
 }
 
-LKF_EXPORT int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *eig, const lkf_image *mask,
-                               int n_masks, float *corners, int32_t *counts, int max_out, lkf_stream stream)
+LKF_EXPORT int lkf_corner_min_eigen_f32(const lkf_image *src, const lkf_image *eig, int block_size, int dy_tail_cols,
+                                        lkf_stream stream)
+{
+    return min_eigen_impl(src, eig, block_size, dy_tail_cols, nullptr, stream);
+}
+
+static int gftt_select_impl(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *eig, const lkf_image *mask,
+                            int n_masks, const int32_t *enable, float *corners, int32_t *counts, int max_out, lkf_stream stream)
 {
     if (!ctx || !p || !img_ok(eig, 1, 4) || !aligned_to(eig, 4) || !corners || !counts || max_out < 1) return LKF_ERR_ARG;
     if (!(p->quality_level > 0) || p->min_distance < 0) return LKF_ERR_ARG;          // cv2 asserts
@@ -390,11 +400,11 @@ LKF_EXPORT int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf
     LKF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)lists * 2 * sizeof(int), s));
     int chunks = (int)((P + 256 * 8 - 1) / (256 * 8));
     if (chunks > 4 * ctx->sm_count) chunks = 4 * ctx->sm_count;
-    k_masked_max<<<dim3(chunks, B), 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, maxkey);
+    k_masked_max<<<dim3(chunks, B), 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, maxkey, enable);
     LKF_LAUNCH_CHECK(ctx);
     dim3 g2((W - 2 + 31) / 32, (H - 2 + 7) / 8, B);
     k_nms_compact<<<g2, 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, maxkey,
-                                     p->quality_level, (unsigned long long *)keys, ccount, cap);
+                                     p->quality_level, (unsigned long long *)keys, ccount, cap, enable);
     LKF_LAUNCH_CHECK(ctx);
     static bool ss_attr = false;
     if (!ss_attr) {
@@ -403,7 +413,29 @@ LKF_EXPORT int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf
     }
     k_sort_select<<<lists, SS_NT, ss_smem, s>>>((unsigned long long *)keys, ccount, cap, W, H, p->max_corners, p->min_distance, cs, gw,
                                                gh, (unsigned *)gaux, (unsigned char *)gaux + (size_t)lists * cap * 4, corners, counts,
-                                               max_out);
+                                               max_out, enable, n_masks);
     LKF_LAUNCH_CHECK(ctx);
     return LKF_OK;
+}
+
+LKF_EXPORT int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *eig, const lkf_image *mask,
+                               int n_masks, float *corners, int32_t *counts, int max_out, lkf_stream stream)
+{
+    return gftt_select_impl(ctx, p, eig, mask, n_masks, nullptr, corners, counts, max_out, stream);
+}
+
+// whole goodFeaturesToTrack for a batch: one eig map per image (workspace), n_masks selections per image,
+// optional per-image predicate evaluated on the device (no host round trip for "refresh only where needed")
+LKF_EXPORT int lkf_gftt_detect(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *src, const lkf_image *mask, int n_masks,
+                               const int32_t *image_enable, float *corners, int32_t *counts, int max_out, lkf_stream stream)
+{
+    if (!ctx || !p || !img_ok(src, 1, 1)) return LKF_ERR_ARG;
+    void *eigbuf;
+    const size_t pitch = ((size_t)src->width * 4 + 15) & ~(size_t)15;
+    int rc = lkf_scratch(ctx, 3, pitch * src->height * src->batch, &eigbuf);
+    if (rc != LKF_OK) return rc;
+    lkf_image eig = {eigbuf, src->batch, src->height, src->width, 1, (int64_t)pitch, (int64_t)(pitch * src->height)};
+    if ((rc = min_eigen_impl(src, &eig, p->block_size, p->dy_tail_cols, image_enable, stream)) != LKF_OK) return rc;
+    lkf_count_launch(ctx);
+    return gftt_select_impl(ctx, p, &eig, mask, n_masks, image_enable, corners, counts, max_out, stream);
 }

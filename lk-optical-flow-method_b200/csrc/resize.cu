@@ -1,0 +1,53 @@
+// resize.cu -- "next" row: imutils.resize(frame, width=860) = cv2.resize(..., INTER_AREA) with a
+// non-integer scale (VP.py:433,531; 1280x720 -> 860x483).  Same float32 operation order as cv2's ResizeArea
+// (oracle lko_resize_area): per source row a horizontal weighted sum accumulated in table order,
+// then a vertical weighted accumulation, then round-half-even + saturate.  No FMA contraction.
+// The coefficient tables are built on the host (double arithmetic, exactly cv2's computeResizeAreaTab).
+#include "common.cuh"
+
+namespace {
+
+// tab: for destination index d the entries [ofs[d], ofs[d+1]) of (src index, alpha)
+__global__ void __launch_bounds__(256)
+k_resize_area(const uint8_t *__restrict__ src, long long srp, long long sip, int cn, uint8_t *__restrict__ dst, long long drp,
+              long long dip, int Hd, int Wd, const int *__restrict__ xofs, const int *__restrict__ xsi,
+              const float *__restrict__ xal, const int *__restrict__ yofs, const int *__restrict__ ysi,
+              const float *__restrict__ yal)
+{
+    const int dx = blockIdx.x * 64 + (threadIdx.x & 63), dy = blockIdx.y * 4 + (threadIdx.x >> 6), b = blockIdx.z;
+    if (dx >= Wd || dy >= Hd) return;
+    const uint8_t *S = src + (long long)b * sip;
+    const int x0 = xofs[dx], x1 = xofs[dx + 1], y0 = yofs[dy], y1 = yofs[dy + 1];
+    for (int c = 0; c < cn; c++) {
+        float sum = 0.f;
+        for (int j = y0; j < y1; j++) {
+            const uint8_t *row = S + (long long)ysi[j] * srp;
+            float buf = 0.f;
+            for (int k = x0; k < x1; k++) buf = __fadd_rn(buf, __fmul_rn((float)row[xsi[k] * cn + c], xal[k]));
+            const float t = __fmul_rn(yal[j], buf);
+            sum = (j == y0) ? t : __fadd_rn(sum, t);
+        }
+        float r = rintf(sum);
+        dst[(long long)b * dip + (long long)dy * drp + dx * cn + c] = (uint8_t)(r < 0.f ? 0.f : (r > 255.f ? 255.f : r));
+    }
+}
+
+}  // namespace
+
+LKF_EXPORT int lkf_resize_area_u8(const lkf_image *src, const lkf_image *dst, const int32_t *xofs, const int32_t *xsi,
+                                  const float *xalpha, const int32_t *yofs, const int32_t *ysi, const float *yalpha,
+                                  lkf_stream stream)
+{
+    if (!src || !dst || !xofs || !xsi || !xalpha || !yofs || !ysi || !yalpha) return LKF_ERR_ARG;
+    if (!img_ok(src, src->channels, 1) || !img_ok(dst, dst->channels, 1) || src->channels != dst->channels ||
+        src->batch != dst->batch || (src->channels != 1 && src->channels != 3))
+        return LKF_ERR_ARG;
+    if (dst->width >= src->width || dst->height >= src->height) return LKF_ERR_UNSUPPORTED;      // area DOWN-scaling only
+    if (src->width % dst->width == 0 && src->height % dst->height == 0) return LKF_ERR_UNSUPPORTED;  // cv2's integer fast path
+    dim3 grid((dst->width + 63) / 64, (dst->height + 3) / 4, dst->batch);
+    k_resize_area<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch, src->channels,
+                                                         (uint8_t *)dst->data, dst->row_pitch, dst->image_pitch, dst->height,
+                                                         dst->width, xofs, xsi, xalpha, yofs, ysi, yalpha);
+    LKF_LAUNCH_CHECK(nullptr);
+    return LKF_OK;
+}

@@ -158,3 +158,73 @@ def gftt_select(eig, masks, max_corners, quality, min_distance, max_out, n_masks
                                  None if md is None else ctypes.byref(md), int(n_masks), corners.data_ptr(),
                                  counts.data_ptr(), int(max_out), stream_ptr()), "lkf_gftt_select")
     return corners, counts
+
+
+def gftt_detect(gray, masks, max_corners, quality, min_distance, block_size, max_out, n_masks=1, enable=None,
+                out=None):
+    """a5+a6 fused for a batch (eig map in the workspace); `enable`: optional int32 [B] device predicate."""
+    ws = Workspace.current()
+    g = _b3(gray)
+    B = g.shape[0]
+    lists = B * n_masks
+    if out is None:
+        corners = torch.empty((lists, max_out, 2), dtype=torch.float32, device=g.device)
+        counts = torch.zeros((lists,), dtype=torch.int32, device=g.device)
+    else:
+        corners, counts = out
+    p = LkfGfttParams(int(max_corners), int(block_size), -1, 0, float(quality), float(min_distance))
+    sd = image_desc(g)
+    md = None if masks is None else image_desc(_b3(masks))
+    check(ws.lib.lkf_gftt_detect(ws.ctx, ctypes.byref(p), ctypes.byref(sd), None if md is None else ctypes.byref(md),
+                                 int(n_masks), None if enable is None else enable.data_ptr(), corners.data_ptr(),
+                                 counts.data_ptr(), int(max_out), stream_ptr()), "lkf_gftt_detect")
+    return corners, counts
+
+
+def area_tables(ssize, dsize):
+    """cv2's computeResizeAreaTab for one axis: (ofs int32 [dsize+1], src index int32, alpha float32)."""
+    import math
+
+    import numpy as np
+    scale = ssize / dsize
+    ofs, si, al = [0], [], []
+    for d in range(dsize):
+        f1 = d * scale
+        f2 = f1 + scale
+        cw = min(scale, ssize - f1)
+        s1 = math.ceil(f1)
+        s2 = min(math.floor(f2), ssize - 1)
+        s1 = min(s1, s2)
+        if s1 - f1 > 1e-3:
+            si.append(s1 - 1); al.append(np.float32((s1 - f1) / cw))
+        for s in range(s1, s2):
+            si.append(s); al.append(np.float32(1.0 / cw))
+        if f2 - s2 > 1e-3:
+            si.append(s2); al.append(np.float32(min(min(f2 - s2, 1.0), cw) / cw))
+        ofs.append(len(si))
+    return (np.asarray(ofs, np.int32), np.asarray(si, np.int32), np.asarray(al, np.float32))
+
+
+_AREA_TABS = {}
+
+
+def resize_area(img, dsize, out=None):
+    """cv2.resize(img, (Wd, Hd), interpolation=INTER_AREA), non-integer down-scale; [B,H,W,3] or [B,H,W] uint8."""
+    ws = Workspace.current()
+    Wd, Hd = int(dsize[0]), int(dsize[1])
+    ch = 3 if (img.dim() == 4 or (img.dim() == 3 and img.shape[-1] == 3 and img.stride(-1) == 1 and img.stride(-2) == 3)) else 1
+    t = img if (img.dim() == 4 or ch == 1 and img.dim() == 3) else img.unsqueeze(0)
+    if ch == 1 and t.dim() == 2:
+        t = t.unsqueeze(0)
+    B, H, W = t.shape[0], t.shape[1], t.shape[2]
+    key = (H, W, Hd, Wd, t.device.index)
+    if key not in _AREA_TABS:
+        xt, yt = area_tables(W, Wd), area_tables(H, Hd)
+        _AREA_TABS[key] = [torch.from_numpy(a).to(t.device) for a in (*xt, *yt)]
+    xo, xs, xa, yo, ys, ya = _AREA_TABS[key]
+    if out is None:
+        out = torch.empty((B, Hd, Wd, 3) if ch == 3 else (B, Hd, Wd), dtype=torch.uint8, device=t.device)
+    s, d = image_desc(t, ch), image_desc(out, ch)
+    check(ws.lib.lkf_resize_area_u8(ctypes.byref(s), ctypes.byref(d), xo.data_ptr(), xs.data_ptr(), xa.data_ptr(),
+                                    yo.data_ptr(), ys.data_ptr(), ya.data_ptr(), stream_ptr()), "lkf_resize_area_u8")
+    return out

@@ -166,3 +166,29 @@ def imutils_resize(img, width):
     h, w = img.shape[:2]
     r = width / float(w)
     return resize_area(img, (width, int(h * r)))
+
+
+class OracleCV:
+    """The oracle behind the four cv2 signatures the scripts call (for oracle/vp_oracle.run_clip)."""
+    COLOR_BGR2GRAY = 6
+    TERM_CRITERIA_EPS = 2
+    TERM_CRITERIA_COUNT = 1
+
+    @staticmethod
+    def cvtColor(img, code):
+        assert code == 6
+        return bgr2gray(img)
+
+    @staticmethod
+    def GaussianBlur(img, ksize, sigma):
+        assert tuple(ksize) == (3, 3) and sigma == 0
+        return blur3(img)
+
+    @staticmethod
+    def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None, blockSize=3):
+        return good_features_to_track(image, maxCorners, qualityLevel, minDistance, mask=mask, blockSize=blockSize)
+
+    @staticmethod
+    def calcOpticalFlowPyrLK(prev, nxt, pts, nextPts, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01), flags=0,
+                             minEigThreshold=1e-4):
+        return pyrlk(prev, nxt, pts, winSize, maxLevel, criteria, flags, minEigThreshold, nextPts)

@@ -1,0 +1,166 @@
+"""GPU parity of the flow -> vanishing-point stage (a8-a13) and of the whole clip loop, through the C ABI.
+
+  * vp_frame kernel vs oracle/vp_oracle.vp_frame on identical synthetic tracks: CSV rows bit-identical (float64),
+    surviving point groups identical -- exercises the checkInside dtype flip (B.1), init aliasing (B.2), the
+    +-1 sigma update (B.3), hide/reset (B.4);
+  * ClipBatchRunner (resize -> ... -> CSV) vs the oracle-driven frame loop on a synthetic zoom clip, and against
+    the golden CSV written by the UNMODIFIED reference script (tolerance: VP within 1 px, north_star).
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _masks():
+    z = np.load(os.path.join(GOLD, "roi_masks_860x483.npz"))
+    return z["mask"], list(z["small"])
+
+
+def _random_tracks(rng, mask, n, foe, lose=0.15, outside=0.1, still=0.05):
+    ys, xs = np.nonzero(mask)
+    idx = rng.integers(0, len(xs), n)
+    p0 = np.stack([xs[idx], ys[idx]], 1).astype(np.float32) + rng.uniform(0, 1, (n, 2)).astype(np.float32)
+    d = p0 - np.asarray(foe, np.float32)
+    p1 = (p0 + d * np.float32(0.02) * rng.uniform(0.2, 3.0, (n, 1)).astype(np.float32)
+          + rng.normal(0, 0.3, (n, 2)).astype(np.float32)).astype(np.float32)
+    out = rng.uniform(size=n) < outside
+    p1[out] += rng.choice([-1, 1], (out.sum(), 2)).astype(np.float32) * np.float32(200)
+    p1[:, 0] = np.clip(p1[:, 0], -20, mask.shape[1] - 1)
+    p1[:, 1] = np.clip(p1[:, 1], -20, mask.shape[0] - 1)
+    same = rng.uniform(size=n) < still
+    p1[same] = p0[same]
+    st = (rng.uniform(size=n) >= lose).astype(np.uint8)
+    return p0, p1, st
+
+
+@pytest.mark.parametrize("variant,tp_num,seed", [("VP", 20, 0), ("LKF", 20, 1), ("VP", 100, 2), ("VP", 20, 3)])
+def test_vp_frame_kernel_matches_oracle(variant, tp_num, seed):
+    import torch
+    from lk_optical_flow_method_b200 import vp as V
+    from oracle import vp_oracle as O
+    mask, small = _masks()
+    B, frames = 3, 140
+    r = V.ClipBatchRunner(B, (483, 860), variant=variant, masks=(mask, small), TP_NUM=tp_num, expected_frames=frames + 8)
+    p = O.params(variant, TP_NUM=tp_num)
+    S = [O.new_state(p) for _ in range(B)]
+    rng = np.random.default_rng(seed)
+    maxp = r.maxp
+    md = V.image_desc(r.mask)
+    for f in range(frames):
+        quiet = 60 <= f < 125 and seed == 3                       # long gap: exercises the hide/reset path
+        P0 = np.zeros((B, 2, maxp, 2), np.float32)
+        P1 = np.zeros_like(P0)
+        ST = np.zeros((B, 2, maxp), np.uint8)
+        C = np.zeros((B, 2), np.int32)
+        host_tracks = []
+        for b in range(B):
+            tr = []
+            for g in range(2):
+                n = 0 if (quiet or rng.uniform() < 0.05) else int(rng.integers(1, maxp + 1))
+                foe = (412 + 5 * b + rng.normal(0, 2), 290 + rng.normal(0, 2))
+                p0, p1, st = _random_tracks(rng, mask, n, foe)
+                if n and rng.uniform() < 0.5:
+                    st[:] = 1                                     # all tracked: the boolean-mask branch of B.1
+                P0[b, g, :n], P1[b, g, :n], ST[b, g, :n], C[b, g] = p0, p1, st, n
+                tr.append((p0, p1, st))
+            host_tracks.append(tr)
+        r.p0.copy_(torch.from_numpy(P0.reshape(B, 2 * maxp, 2)))
+        r.p1.copy_(torch.from_numpy(P1.reshape(B, 2 * maxp, 2)))
+        r.st.copy_(torch.from_numpy(ST.reshape(B, 2 * maxp)))
+        r.counts.copy_(torch.from_numpy(C.reshape(-1)))
+        from lk_optical_flow_method_b200._lib import check
+        from lk_optical_flow_method_b200.device import stream_ptr
+        check(r.ws.lib.lkf_vp_frame(ctypes.byref(r.vp_params), r.states.data_ptr(), B, r.p0.data_ptr(), r.p1.data_ptr(),
+                                    r.st.data_ptr(), r.counts.data_ptr(), maxp, ctypes.byref(md), r.rows.data_ptr(), r.row_cap,
+                                    r.refresh.data_ptr(), None, stream_ptr()), "lkf_vp_frame")
+        new_counts = r.counts.cpu().numpy().reshape(B, 2)
+        new_p0 = r.p0.cpu().numpy().reshape(B, 2, maxp, 2)
+        refresh = r.refresh.cpu().numpy()
+        for b in range(B):
+            tracks, lens = [], []
+            any_pts = any(len(t[0]) for t in host_tracks[b])
+            for g, (p0, p1, st) in enumerate(host_tracks[b]):
+                if len(p0) == 0 or not any_pts:
+                    tracks.append((np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32)))
+                    lens.append(len(p0))
+                    continue
+                s = O.apply_roi_filter(p1.reshape(-1, 1, 2), st.reshape(-1, 1).copy(), mask)
+                keep = s.ravel() == 1
+                tracks.append((p0[keep], p1[keep]))
+                lens.append(int(keep.sum()))
+                assert new_counts[b, g] == keep.sum()
+                assert np.array_equal(new_p0[b, g, :keep.sum()], p1[keep])
+            O.vp_frame(S[b], tracks if any_pts else [], p, 483)
+            want_refresh = (lens[0] + lens[1]) < p["TP_NUM"] * p["TP_UPDATE_RATE"] or S[b]["tp_ult"] == p["TP_UPDATE_TIME"]
+            assert bool(refresh[b]) == bool(want_refresh)
+            if want_refresh:
+                S[b]["tp_ult"] = 0
+            S[b]["tp_ult"] += 1
+            S[b]["vp_ult"] += 1
+    got = r.rows_host()
+    states = r.state_structs()
+    total = 0
+    for b in range(B):
+        want = np.array(S[b]["rows"], np.float64).reshape(-1, 2)
+        assert got[b].shape == want.shape, (got[b].shape, want.shape)
+        assert np.array_equal(got[b], want, equal_nan=True)        # bit-identical CSV rows
+        assert states[b].n_lines == S[b]["n_lines"] and states[b].n_cps == S[b]["n_cps"]
+        total += len(want)
+    assert total > 50
+    from lk_optical_flow_method_b200.vp import csv_text
+    assert csv_text(got[0]) == O.csv_text(S[0]["rows"])           # a13: same bytes, \r\n line ends
+    assert csv_text(got[0]).startswith("x,y\r\n")
+
+
+def test_resize_area_bit_exact(oracle):
+    import torch
+    from lk_optical_flow_method_b200 import ops, synth
+    tex = synth.make_texture(320, 180, 4)
+    f = np.stack([synth.zoom_frame(tex, 320, 180, t) for t in (2, 9)])
+    d = torch.from_numpy(f).cuda()
+    for (wd, hd) in [(215, 120), (200, 113), (107, 61)]:
+        got = ops.resize_area(d, (wd, hd)).cpu().numpy()
+        assert np.array_equal(got, np.stack([oracle.resize_area(x, (wd, hd)) for x in f]))
+    g = torch.from_numpy(np.ascontiguousarray(f[..., 1])).cuda()
+    assert np.array_equal(ops.resize_area(g, (215, 120)).cpu().numpy(), np.stack([oracle.resize_area(x, (215, 120)) for x in f[..., 1]]))
+
+
+def _clip(meta, n):
+    from lk_optical_flow_method_b200 import synth
+    tex = synth.make_texture(meta["W"], meta["H"], meta["clip"].get("seed", 0))
+    kw = {k: v for k, v in meta["clip"].items() if k != "seed"}
+    return [synth.zoom_frame(tex, meta["W"], meta["H"], t, **kw) for t in range(n)]
+
+
+@pytest.mark.parametrize("name", ["vp_zoom60", "lkf_zoom60", "vp_zoom60_tp100", "vp_fast40"])
+def test_clip_runner_vs_oracle_loop_and_golden(oracle, name):
+    import torch
+    from lk_optical_flow_method_b200 import vp as V
+    from oracle import vp_oracle as O
+    meta = json.load(open(os.path.join(GOLD, f"{name}.json")))
+    frames = _clip(meta, meta["frames"])
+    variant = "LKF" if meta["script"].startswith("LK_Final") else "VP"
+    ov = meta["overrides"]
+    masks = _masks()
+    # two copies of the clip in one batch: clips are independent, results must be identical
+    batches = (torch.from_numpy(np.stack([f, f])).cuda() for f in frames)
+    rows, runner = V.run_clips(batches, variant=variant, masks=masks, expected_frames=meta["frames"] + 4, **ov)
+    assert np.array_equal(rows[0], rows[1])
+    ref = O.run_clip(frames, oracle.OracleCV, variant=variant, masks=masks, **ov)
+    want = np.array(ref["rows"], np.float64).reshape(-1, 2)
+    assert rows[0].shape == want.shape
+    assert np.array_equal(rows[0], want)                           # same arithmetic end to end -> same rows
+    gold = np.loadtxt(os.path.join(GOLD, f"{name}.csv"), delimiter=",", skiprows=1).reshape(-1, 2)
+    assert len(gold) == meta["rows"]
+    # against the unmodified script (cv2 arithmetic): VP within 1 px (north_star); rows line up one-to-one
+    assert rows[0].shape == gold.shape, (rows[0].shape, gold.shape)
+    if len(gold):
+        assert np.abs(rows[0] - gold).max() <= 1.0

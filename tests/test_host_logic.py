@@ -1,0 +1,64 @@
+"""Host-side logic that needs no GPU: argument validation of the cv2-signature boundary, the synthetic
+clip generator, pyramid geometry."""
+import numpy as np
+import pytest
+
+
+def test_boundary_argument_errors_before_any_device_work():
+    import lk_optical_flow_method_b200.cv as cv
+    img = np.zeros((48, 64), np.uint8)
+    pts = np.zeros((4, 1, 2), np.float32)
+    lk = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.03))
+    assert cv.calcOpticalFlowPyrLK(img, img, np.zeros((0, 1, 2), np.float32), None, **lk) == (None, None, None)
+    with pytest.raises(cv.error):
+        cv.calcOpticalFlowPyrLK(img, img, pts.astype(np.float64), None, **lk)
+    with pytest.raises(cv.error):
+        cv.calcOpticalFlowPyrLK(img, img, np.zeros((8, 1, 2), np.float32)[::2], None, **lk)
+    with pytest.raises(cv.error):
+        cv.calcOpticalFlowPyrLK(img, img[:-1], pts, None, **lk)
+    with pytest.raises(cv.error):
+        cv.calcOpticalFlowPyrLK(img, img, pts, None, winSize=(2, 9))
+    with pytest.raises(cv.error):
+        cv.calcOpticalFlowPyrLK(img.astype(np.float32), img, pts, None, **lk)
+    with pytest.raises(cv.error):
+        cv.goodFeaturesToTrack(img, 10, 0.0, 7)
+    with pytest.raises(cv.error):
+        cv.goodFeaturesToTrack(img, 10, 0.1, -1)
+    with pytest.raises(cv.error):
+        cv.goodFeaturesToTrack(img, 10, 0.1, 7, useHarrisDetector=True)
+    with pytest.raises(cv.error):
+        cv.goodFeaturesToTrack(img, 10, 0.1, 7, mask=np.zeros((3, 3), np.uint8))
+    with pytest.raises(cv.error):
+        cv.cvtColor(np.zeros((8, 8, 3), np.uint8), 4)
+    with pytest.raises(cv.error):
+        cv.GaussianBlur(img, (5, 5), 0)
+    assert cv.COLOR_BGR2GRAY == 6 and cv.TERM_CRITERIA_EPS == 2 and cv.TERM_CRITERIA_COUNT == 1
+
+
+def test_forwarding_of_non_hot_path_attributes():
+    cv2 = pytest.importorskip("cv2")
+    import lk_optical_flow_method_b200.cv as cv
+    assert cv.fillPoly is cv2.fillPoly and cv.VideoCapture is cv2.VideoCapture
+
+
+def test_synth_is_deterministic_and_device_independent():
+    import torch
+    from lk_optical_flow_method_b200 import synth
+    tex = synth.make_texture(160, 96, 5)
+    assert tex.shape == (192, 320, 3) and tex.dtype == np.uint8
+    assert np.array_equal(tex, synth.make_texture(160, 96, 5))
+    f = synth.zoom_frame(tex, 160, 96, 7)
+    ft = synth.zoom_frame(torch.from_numpy(tex), 160, 96, 7)
+    assert np.array_equal(f, ft.numpy())
+    # the focus of expansion maps to the same texture point in every frame of a period
+    W, H = 160, 96
+    fx, fy = synth.foe_px(W, H)
+    a = synth.zoom_frame(tex, W, H, 0)[int(fy), int(fx)].astype(int)
+    b = synth.zoom_frame(tex, W, H, 20)[int(fy), int(fx)].astype(int)
+    assert np.abs(a - b).max() <= 24
+
+
+def test_pyramid_shapes():
+    from lk_optical_flow_method_b200.device import pyramid_shapes
+    assert pyramid_shapes(483, 860, 3) == [(483, 860), (242, 430), (121, 215)]
+    assert pyramid_shapes(1080, 1920, 3) == [(1080, 1920), (540, 960), (270, 480)]
