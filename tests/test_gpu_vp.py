@@ -48,7 +48,8 @@ def test_vp_frame_kernel_matches_oracle(variant, tp_num, seed):
     from oracle import vp_oracle as O
     mask, small = _masks()
     B, frames = 3, 140
-    r = V.ClipBatchRunner(B, (483, 860), variant=variant, masks=(mask, small), TP_NUM=tp_num, expected_frames=frames + 8)
+    r = V.ClipBatchRunner(B, (720, 1280), variant=variant,   # Hei = int(860*720/1280) = 483 like the script
+                          masks=(mask, small), TP_NUM=tp_num, expected_frames=frames + 8)
     p = O.params(variant, TP_NUM=tp_num)
     S = [O.new_state(p) for _ in range(B)]
     rng = np.random.default_rng(seed)
@@ -105,6 +106,18 @@ def test_vp_frame_kernel_matches_oracle(variant, tp_num, seed):
                 S[b]["tp_ult"] = 0
             S[b]["tp_ult"] += 1
             S[b]["vp_ult"] += 1
+        sts = r.state_structs()
+        for b in range(B):
+            if sts[b].n_rows != len(S[b]["rows"]) and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+                import pickle
+                got_rows = r.rows.cpu().numpy()[b, :sts[b].n_rows]
+                with open(os.path.join(ROOT, "gpurun_out", "vp_mismatch.pkl"), "wb") as fh:
+                    pickle.dump(dict(frame=f, clip=b, tracks=host_tracks[b], gpu_rows=got_rows, ref_rows=S[b]["rows"],
+                                     gpu=(sts[b].n_rows, sts[b].n_lines, sts[b].n_cps, sts[b].vp_x, sts[b].vp_y, sts[b].vp_init,
+                                          list(sts[b].avg_len)),
+                                     ref=(len(S[b]["rows"]), S[b]["n_lines"], S[b]["n_cps"], S[b]["vp"], S[b]["avg"])), fh)
+            assert sts[b].n_rows == len(S[b]["rows"]), (f, b, sts[b].n_rows, len(S[b]["rows"]), sts[b].n_lines, S[b]["n_lines"],
+                                                         sts[b].n_cps, S[b]["n_cps"], host_tracks[b])
     got = r.rows_host()
     states = r.state_structs()
     total = 0
