@@ -222,6 +222,179 @@ __global__ void __launch_bounds__(NT) k_scharr(SrcU8 src0, long long src_ip, Img
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a1+a2 (and a2) streaming form for 16-byte aligned rows with W % 16 == 0 (1080p, 4K, pyramid levels):
+// no shared memory, no barriers.  A thread owns 16 consecutive columns and slides down R rows; per input
+// row it loads 48 B of BGR as 3 x 128-bit (or 16 B of gray), converts 16 + 2 pixels (the two neighbours
+// come from one aligned 32-bit load each), forms the horizontal [1 2 1] sums packed two per register
+// and keeps the last two rows of sums in registers; the vertical [1 2 1] pass, rounding and byte packing
+// run on the packed pairs.  Gray uses two DP4A with the weights split as w = 128*wh + wl.
+// ---------------------------------------------------------------------------------------------
+constexpr int SV_NT = 128, SV_PX = 16;
+
+// (3735, 19235, 9798) = 128*(29, 150, 76) + (23, 35, 70); byte k of a word multiplies byte k of the weights
+__device__ __forceinline__ uint32_t gray_dp(uint32_t pix_lo3)
+{   // B,G,R in bytes 0,1,2 (byte 3 ignored)
+    const uint32_t WH = 29u | (150u << 8) | (76u << 16), WL = 23u | (35u << 8) | (70u << 16);
+    uint32_t lo = __dp4a(pix_lo3, WL, 16384u), hi = __dp4a(pix_lo3, WH, 0u);
+    return (lo + (hi << 7)) >> 15;
+}
+__device__ __forceinline__ uint32_t gray_dp_hi3(uint32_t pix_hi3)
+{   // B,G,R in bytes 1,2,3 (byte 0 ignored)
+    const uint32_t WH = (29u << 8) | (150u << 16) | (76u << 24), WL = (23u << 8) | (35u << 16) | (70u << 24);
+    uint32_t lo = __dp4a(pix_hi3, WL, 16384u), hi = __dp4a(pix_hi3, WH, 0u);
+    return (lo + (hi << 7)) >> 15;
+}
+
+// 16 gray values of columns x0..x0+15 plus the neighbours g[-1], g[16]; g as 18 ints (index j+1)
+struct RowBGR {
+    __device__ __forceinline__ static void load(const uint8_t *__restrict__ row, int x0, int W, uint32_t (&g)[18])
+    {
+        const uint4 *q = reinterpret_cast<const uint4 *>(row + 3 * x0);
+        const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+        const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t a = w[3 * k], b = w[3 * k + 1], c = w[3 * k + 2];
+            g[4 * k + 1] = gray_dp(a);                                   // bytes 0..2 of a
+            g[4 * k + 2] = gray_dp(__byte_perm(a, b, 0x0543));           // a3 b0 b1
+            g[4 * k + 3] = gray_dp(__byte_perm(b, c, 0x0432));           // b2 b3 c0
+            g[4 * k + 4] = gray_dp_hi3(c);                               // bytes 1..3 of c
+        }
+        if (x0 > 0) g[0] = gray_dp_hi3(__ldg(reinterpret_cast<const uint32_t *>(row + 3 * x0 - 4)));
+        else g[0] = g[2];                                                // REFLECT_101: column -1 -> 1
+        if (x0 + SV_PX < W) g[17] = gray_dp(__ldg(reinterpret_cast<const uint32_t *>(row + 3 * x0 + 48)));
+        else g[17] = g[15];                                              // column W -> W-2
+    }
+};
+struct RowU8 {
+    __device__ __forceinline__ static void load(const uint8_t *__restrict__ row, int x0, int W, uint32_t (&g)[18])
+    {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + x0));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            g[4 * k + 1] = w[k] & 255u; g[4 * k + 2] = (w[k] >> 8) & 255u; g[4 * k + 3] = (w[k] >> 16) & 255u; g[4 * k + 4] = w[k] >> 24;
+        }
+        g[0] = x0 > 0 ? (uint32_t)__ldg(row + x0 - 1) : g[2];
+        g[17] = x0 + SV_PX < W ? (uint32_t)__ldg(row + x0 + 16) : g[15];
+    }
+};
+
+template <class Row>
+__device__ __forceinline__ void hsum_row(const uint8_t *__restrict__ row, int x0, int W, uint32_t (&h)[8])
+{
+    uint32_t g[18];
+    Row::load(row, x0, W, g);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t a = g[2 * k] + 2u * g[2 * k + 1] + g[2 * k + 2];       // column 2k
+        uint32_t b = g[2 * k + 1] + 2u * g[2 * k + 2] + g[2 * k + 3];   // column 2k+1
+        h[k] = a | (b << 16);
+    }
+}
+
+template <class Row>
+__global__ void __launch_bounds__(SV_NT) k_blur3_stream(const uint8_t *__restrict__ src, long long srp, long long sip,
+                                                        uint8_t *__restrict__ dst, long long drp, long long dip, int H, int W,
+                                                        int rows_per_block)
+{
+    const int x0 = (blockIdx.x * SV_NT + threadIdx.x) * SV_PX;
+    if (x0 >= W) return;
+    const int b = blockIdx.z;
+    const uint8_t *S = src + (long long)b * sip;
+    uint8_t *D = dst + (long long)b * dip + x0;
+    const int y0 = blockIdx.y * rows_per_block, y1 = min(H, y0 + rows_per_block);
+    uint32_t hm[8], hc[8], hp[8];
+    hsum_row<Row>(S + (long long)reflect101(y0 - 1, H) * srp, x0, W, hm);
+    hsum_row<Row>(S + (long long)y0 * srp, x0, W, hc);
+    for (int y = y0; y < y1; y++) {
+        hsum_row<Row>(S + (long long)reflect101(y + 1, H) * srp, x0, W, hp);
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            // packed pairs: (hm + 2 hc + hp + 8) >> 4, no carry between the 16-bit halves (max 4080 + 8)
+            uint32_t v0 = ((hm[2 * k] + hp[2 * k] + 0x00080008u + 2u * hc[2 * k]) >> 4) & 0x00ff00ffu;
+            uint32_t v1 = ((hm[2 * k + 1] + hp[2 * k + 1] + 0x00080008u + 2u * hc[2 * k + 1]) >> 4) & 0x00ff00ffu;
+            o[k] = __byte_perm(v0, v1, 0x6420);
+        }
+        *reinterpret_cast<uint4 *>(D + (long long)y * drp) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { hm[k] = hc[k]; hc[k] = hp[k]; }
+    }
+}
+
+template <class Row>
+int launch_blur3_stream(const lkf_image *src, const lkf_image *dst, cudaStream_t s)
+{
+    const int H = dst->height, W = dst->width, R = 32;
+    dim3 grid((W / SV_PX + SV_NT - 1) / SV_NT, (H + R - 1) / R, dst->batch);
+    k_blur3_stream<Row><<<grid, SV_NT, 0, s>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch, (uint8_t *)dst->data,
+                                               dst->row_pitch, dst->image_pitch, H, W, R);
+    return LKF_OK;
+}
+
+bool stream_ok(const lkf_image *src, const lkf_image *dst)
+{
+    return dst->width % SV_PX == 0 && dst->width >= 2 * SV_PX && dst->height >= 2 && aligned_to(src, 16) && aligned_to(dst, 16);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a3 streaming form (source rows 16-byte aligned, W_src % 16 == 0): a thread owns 8 output columns
+// (16 source columns + 2 left + 1 right neighbour), slides down; the horizontal [1 4 6 4 1] sums of a
+// source row are packed two per register (<= 4080), five rows of them live in registers, and the
+// vertical pass + rounding run on the packed pairs (16*4080 + 128 < 2^16, no carry between halves).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pd_hsum_row(const uint8_t *__restrict__ row, int xs, int Ws, uint32_t (&h)[4])
+{
+    // source columns xs-2 .. xs+16 -> g[0..18]
+    uint32_t g[19];
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + xs));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        g[4 * k + 2] = w[k] & 255u; g[4 * k + 3] = (w[k] >> 8) & 255u; g[4 * k + 4] = (w[k] >> 16) & 255u; g[4 * k + 5] = w[k] >> 24;
+    }
+    if (xs > 0) {
+        const uint32_t l = __ldg(reinterpret_cast<const uint32_t *>(row + xs - 4));
+        g[0] = (l >> 16) & 255u; g[1] = l >> 24;
+    } else { g[0] = g[4]; g[1] = g[3]; }                                  // columns -2,-1 -> 2,1
+    g[18] = xs + 16 < Ws ? (uint32_t)__ldg(row + xs + 16) : g[16];          // column Ws -> Ws-2
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t a = g[4 * k] + g[4 * k + 4] + 4u * (g[4 * k + 1] + g[4 * k + 3]) + 6u * g[4 * k + 2];
+        uint32_t b = g[4 * k + 2] + g[4 * k + 6] + 4u * (g[4 * k + 3] + g[4 * k + 5]) + 6u * g[4 * k + 4];
+        h[k] = a | (b << 16);
+    }
+}
+
+__global__ void __launch_bounds__(SV_NT) k_pyrdown_stream(const uint8_t *__restrict__ src, long long srp, long long sip,
+                                                          uint8_t *__restrict__ dst, long long drp, long long dip, int Hs, int Ws,
+                                                          int Hd, int Wd, int rows_per_block)
+{
+    const int xo = (blockIdx.x * SV_NT + threadIdx.x) * 8;
+    if (xo >= Wd) return;
+    const int b = blockIdx.z, xs = 2 * xo;
+    const uint8_t *S = src + (long long)b * sip;
+    uint8_t *D = dst + (long long)b * dip + xo;
+    const int y0 = blockIdx.y * rows_per_block, y1 = min(Hd, y0 + rows_per_block);
+    uint32_t r0[4], r1[4], r2[4], r3[4], r4[4];
+    pd_hsum_row(S + (long long)reflect101(2 * y0 - 2, Hs) * srp, xs, Ws, r0);
+    pd_hsum_row(S + (long long)reflect101(2 * y0 - 1, Hs) * srp, xs, Ws, r1);
+    pd_hsum_row(S + (long long)reflect101(2 * y0, Hs) * srp, xs, Ws, r2);
+    for (int y = y0; y < y1; y++) {
+        pd_hsum_row(S + (long long)reflect101(2 * y + 1, Hs) * srp, xs, Ws, r3);
+        pd_hsum_row(S + (long long)reflect101(2 * y + 2, Hs) * srp, xs, Ws, r4);
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            o[k] = ((r0[k] + r4[k] + 0x00800080u + 4u * (r1[k] + r3[k]) + 6u * r2[k]) >> 8) & 0x00ff00ffu;
+        *reinterpret_cast<uint2 *>(D + (long long)y * drp) = make_uint2(__byte_perm(o[0], o[1], 0x6420), __byte_perm(o[2], o[3], 0x6420));
+#pragma unroll
+        for (int k = 0; k < 4; k++) { r0[k] = r2[k]; r1[k] = r3[k]; r2[k] = r4[k]; }
+    }
+}
+
 bool same_geometry(const lkf_image *a, const lkf_image *b)
 {
     return a->batch == b->batch && a->height == b->height && a->width == b->width;
@@ -243,6 +416,11 @@ LKF_EXPORT int lkf_bgr2gray_u8(const lkf_image *bgr, const lkf_image *gray, lkf_
 LKF_EXPORT int lkf_gaussian_blur3_u8(const lkf_image *src, const lkf_image *dst, lkf_stream stream)
 {
     if (!img_ok(src, 1, 1) || !img_ok(dst, 1, 1) || !same_geometry(src, dst) || src->data == dst->data) return LKF_ERR_ARG;
+    if (stream_ok(src, dst)) {
+        launch_blur3_stream<RowU8>(src, dst, (cudaStream_t)stream);
+        LKF_LAUNCH_CHECK(nullptr);
+        return LKF_OK;
+    }
     Img d = to_img(dst);
     SrcU8 s{(const uint8_t *)src->data, src->row_pitch, src->height, src->width, aligned_to(src, 4)};
     dim3 grid((d.W + BT_W - 1) / BT_W, (d.H + BT_H - 1) / BT_H, d.B);
@@ -254,6 +432,11 @@ LKF_EXPORT int lkf_gaussian_blur3_u8(const lkf_image *src, const lkf_image *dst,
 LKF_EXPORT int lkf_process_img_u8(const lkf_image *bgr, const lkf_image *dst, lkf_stream stream)
 {
     if (!img_ok(bgr, 3, 1) || !img_ok(dst, 1, 1) || !same_geometry(bgr, dst)) return LKF_ERR_ARG;
+    if (stream_ok(bgr, dst)) {
+        launch_blur3_stream<RowBGR>(bgr, dst, (cudaStream_t)stream);
+        LKF_LAUNCH_CHECK(nullptr);
+        return LKF_OK;
+    }
     Img d = to_img(dst);
     SrcBGR s{(const uint8_t *)bgr->data, bgr->row_pitch, bgr->height, bgr->width, aligned_to(bgr, 4)};
     dim3 grid((d.W + BT_W - 1) / BT_W, (d.H + BT_H - 1) / BT_H, d.B);
@@ -267,6 +450,15 @@ LKF_EXPORT int lkf_pyr_down_u8(const lkf_image *src, const lkf_image *dst, lkf_s
     if (!img_ok(src, 1, 1) || !img_ok(dst, 1, 1) || src->batch != dst->batch ||
         dst->height != (src->height + 1) / 2 || dst->width != (src->width + 1) / 2)
         return LKF_ERR_ARG;
+    if (src->width % 16 == 0 && src->width >= 32 && src->height >= 4 && aligned_to(src, 16) && aligned_to(dst, 8)) {
+        const int R = 16;
+        dim3 g((dst->width / 8 + SV_NT - 1) / SV_NT, (dst->height + R - 1) / R, dst->batch);
+        k_pyrdown_stream<<<g, SV_NT, 0, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch,
+                                                                (uint8_t *)dst->data, dst->row_pitch, dst->image_pitch, src->height,
+                                                                src->width, dst->height, dst->width, R);
+        LKF_LAUNCH_CHECK(nullptr);
+        return LKF_OK;
+    }
     Img d = to_img(dst);
     SrcU8 s{(const uint8_t *)src->data, src->row_pitch, src->height, src->width, aligned_to(src, 4)};
     dim3 grid((d.W + PD_W - 1) / PD_W, (d.H + PD_H - 1) / PD_H, d.B);
