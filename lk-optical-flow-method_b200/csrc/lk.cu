@@ -258,7 +258,7 @@ k_lk_track(LKLevels lv, int n_levels, int w, int h, int max_count, double eps2, 
 // per-warp shared-memory tile (window + MARGIN on every side, loaded once per level with aligned
 // 32-bit loads and re-centred only if the iterate walks out of it).
 // ---------------------------------------------------------------------------------------------
-constexpr int LKT_WARPS = 4;     // small CTAs: a CTA retires when its slowest feature converges
+constexpr int LKT_WARPS = 2;     // small CTAs: a CTA retires when its slowest feature converges
 
 template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_>
 struct LKT {
@@ -266,7 +266,12 @@ struct LKT {
     static constexpr int RPR = WW / RUN;                 // runs per window row
     static constexpr int NRUNS = RPR * WH;
     static constexpr int RPL = (NRUNS + 31) / 32;        // runs per lane
-    static constexpr int RW = WW + 3, RH = WH + 3, RWP = (RW + 3) & ~3;
+    static constexpr int RW = WW + 3, RH = WH + 3;
+    static constexpr int RWW = (RW + 3 + 3) / 4;                      // words per raw row incl. up to 3 bytes of alignment slack
+    static constexpr int RWP = RWW * 4;                               // raw pitch (bytes)
+    static constexpr int RAW_LPR = RWW <= 8 ? 8 : 16;                 // lanes per raw row (power of two)
+    static constexpr int TILE_WPR = TWC_ / 4;
+    static constexpr int TILE_LPR = TILE_WPR <= 8 ? 8 : (TILE_WPR <= 16 ? 16 : 32);
     static constexpr int DW = WW + 1, DH = WH + 1, DWP = DWP_;      // DWP: der pitch (words), chosen bank-conflict-poor
     static constexpr int TWC = TWC_;                                  // tile pitch (bytes), multiple of 4
     static constexpr int TH = WH + 1 + 2 * MARGIN;
@@ -277,6 +282,7 @@ struct LKT {
     static_assert(AREA <= 2048, "int32 lane partials");
     static_assert(TWC % 4 == 0 && TWC >= WW + 1 + 2 * MARGIN + 3, "tile pitch");
     static_assert(DWP >= DW, "der pitch");
+    static_assert(RWW <= 16 && TILE_WPR <= 32, "loader lane mapping");
 };
 
 // tile origin: window + MARGIN, x aligned down to 4; slid back inside the level when the window itself is inside
@@ -294,25 +300,63 @@ __device__ __forceinline__ void place_tile(int ix, int iy, int W, int H, int &tx
     if (iy >= 0 && iy + WH1 <= H && H >= T::TH) ty0 = min(max(ty0, 0), H - T::TH);
 }
 
+// `next` tile: TILE_LPR lanes per row (TILE_WPR of them load one aligned 32-bit word), 32/TILE_LPR rows per pass;
+// all loads of the tile are issued before the first store (one memory round trip instead of one per pass).
 template <class T>
 __device__ __forceinline__ void load_j_tile(const uint8_t *__restrict__ J, long long rp, int W, int H, bool al4,
                                             int tx0, int ty0, unsigned char *tile, int lane)
 {
-    constexpr int WPR = T::TWC / 4;
     const bool inside = tx0 >= 0 && ty0 >= 0 && tx0 + T::TWC <= W && ty0 + T::TH <= H;
     if (inside && al4) {
-        const uint8_t *base = J + (long long)ty0 * rp + tx0;
-#pragma unroll 4
-        for (int i = lane; i < WPR * T::TH; i += 32) {
-            int r = i / WPR, k = i - r * WPR;
-            reinterpret_cast<uint32_t *>(tile)[i] = __ldg(reinterpret_cast<const uint32_t *>(base + (long long)r * rp) + k);
-        }
+        constexpr int RPP = 32 / T::TILE_LPR, NP = (T::TH + RPP - 1) / RPP;
+        const int k = lane & (T::TILE_LPR - 1), r0 = lane / T::TILE_LPR;
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(J + (long long)(ty0 + r0) * rp + tx0) + k;
+        const long long step = (rp * RPP) >> 2;
+        uint32_t v[NP];
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+            if (k < T::TILE_WPR && r0 + q * RPP < T::TH) v[q] = __ldg(base + q * step);
+        uint32_t *t = reinterpret_cast<uint32_t *>(tile) + r0 * T::TILE_WPR + k;
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+            if (k < T::TILE_WPR && r0 + q * RPP < T::TH) t[q * RPP * T::TILE_WPR] = v[q];
     } else {
-        for (int i = lane; i < T::TWC * T::TH; i += 32) {
-            int r = i / T::TWC, c = i - r * T::TWC;
-            tile[i] = J[(long long)reflect101(ty0 + r, H) * rp + reflect101(tx0 + c, W)];
+        // mirrored path: a lane owns columns (reflect once per column), rows in the inner loop
+        for (int c = lane; c < T::TWC; c += 32) {
+            const uint8_t *col = J + reflect101(tx0 + c, W);
+            for (int r = 0; r < T::TH; r++) tile[r * T::TWC + c] = col[(long long)reflect101(ty0 + r, H) * rp];
         }
     }
+}
+
+// template neighbourhood: rows ipy-1 .. ipy+WH+1, columns from the 4-aligned ax <= ipx-1; returns the byte offset of
+// column ipx-1 inside a raw row (0..3 on the aligned path, 0 on the mirrored path)
+template <class T>
+__device__ __forceinline__ int load_raw(const uint8_t *__restrict__ I, long long rp, int W, int H, bool al4, int ipx, int ipy,
+                                        unsigned char *raw, int lane)
+{
+    const int ax = ((ipx - 1) >> 2) << 2;
+    const bool inside = al4 && ax >= 0 && ipy >= 1 && ax + T::RWP <= W && ipy + T::RH - 2 < H;
+    if (inside) {
+        constexpr int RPP = 32 / T::RAW_LPR, NP = (T::RH + RPP - 1) / RPP;
+        const int k = lane & (T::RAW_LPR - 1), r0 = lane / T::RAW_LPR;
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(I + (long long)(ipy - 1 + r0) * rp + ax) + k;
+        const long long step = (rp * RPP) >> 2;
+        uint32_t v[NP];
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+            if (k < T::RWW && r0 + q * RPP < T::RH) v[q] = __ldg(base + q * step);
+        uint32_t *t = reinterpret_cast<uint32_t *>(raw) + r0 * T::RWW + k;
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+            if (k < T::RWW && r0 + q * RPP < T::RH) t[q * RPP * T::RWW] = v[q];
+        return (ipx - 1) - ax;
+    }
+    for (int c = lane; c < T::RW; c += 32) {
+        const uint8_t *col = I + reflect101(ipx - 1 + c, W);
+        for (int r = 0; r < T::RH; r++) raw[r * T::RWP + c] = col[(long long)reflect101(ipy - 1 + r, H) * rp];
+    }
+    return 0;
 }
 
 template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, int MINB>
@@ -320,7 +364,7 @@ __global__ void __launch_bounds__(LKT_WARPS * 32, MINB)
 k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, double min_eig_thr,
              const float *__restrict__ prev_pts, const int *__restrict__ counts, int max_pts,
              float *__restrict__ next_pts, uint8_t *__restrict__ status, float *__restrict__ err,
-             int *__restrict__ iters_out, unsigned al4_mask)
+             int *__restrict__ iters_out, unsigned al4_mask, unsigned ial4_mask)
 {
     using T = LKT<WW, WH, RUN, MARGIN, DWP_, TWC_>;
     extern __shared__ __align__(16) unsigned char smem_all[];
@@ -361,7 +405,7 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
         const uint8_t *I = lv.prev[l] + (long long)b * lv.pip[l];
         const uint8_t *J = lv.next[l] + (long long)b * lv.nip[l];
         const long long irp = lv.prp[l], jrp = lv.nrp[l];
-        const bool jal4 = (al4_mask >> l) & 1u;
+        const bool jal4 = (al4_mask >> l) & 1u, ial4 = (ial4_mask >> l) & 1u;
         const float sc = 1.f / (float)(1 << l);
         float px = __fmul_rn(ppx, sc), py = __fmul_rn(ppy, sc);
         float nx, ny;
@@ -387,39 +431,33 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
             place_tile<T>(__float2int_rd(fx), __float2int_rd(fy), W, H, tx0, ty0);
             load_j_tile<T>(J, jrp, W, H, jal4, tx0, ty0, tile, lane);
         }
-        // 1. raw (WW+3)x(WH+3) neighbourhood of prev, mirrored
-        {
-            const bool inside = ipx >= 1 && ipy >= 1 && ipx + WW + 1 < W && ipy + WH + 1 < H;
-            if (inside) {
-                const uint8_t *base = I + (long long)(ipy - 1) * irp + (ipx - 1);
-#pragma unroll 6
-                for (int idx = lane; idx < T::RW * T::RH; idx += 32) {
-                    int j = idx / T::RW, i = idx - j * T::RW;
-                    raw[j * T::RWP + i] = __ldg(base + (long long)j * irp + i);
-                }
-            } else {
-                for (int idx = lane; idx < T::RW * T::RH; idx += 32) {
-                    int j = idx / T::RW, i = idx - j * T::RW;
-                    raw[j * T::RWP + i] = I[(long long)reflect101(ipy - 1 + j, H) * irp + reflect101(ipx - 1 + i, W)];
-                }
-            }
-        }
+        // 1. raw (WW+3)x(WH+3) neighbourhood of prev (aligned words, or mirrored bytes near the border)
+        const int ro = load_raw<T>(I, irp, W, H, ial4, ipx, ipy, raw, lane);
         __syncwarp();
-        // 2. Scharr on the (WW+1)x(WH+1) sample grid, zero outside the level
+        // 2. Scharr on the (WW+1)x(WH+1) sample grid, zero outside the level.  A lane owns a column and slides down
+        //    the rows keeping the last two row terms: Ix = 3 dx(j) + 10 dx(j+1) + 3 dx(j+2), Iy = S(j+2) - S(j).
         {
+            constexpr int G = T::DW <= 16 ? 2 : 1;                 // column groups that split the rows (narrow windows)
+            constexpr int LPG = 32 / G, RPG = (T::DH + G - 1) / G;
+            const int i = lane % LPG, grp = lane / LPG;
+            const int j0 = grp * RPG, j1 = min(T::DH, j0 + RPG);
             const bool inside = ipx >= 0 && ipy >= 0 && ipx + WW < W && ipy + WH < H;
+            if (i < T::DW) {
+                const unsigned char *rp0 = raw + j0 * T::RWP + ro + i;
+                int d0 = (int)rp0[2] - (int)rp0[0], s0 = 3 * ((int)rp0[0] + (int)rp0[2]) + 10 * (int)rp0[1];
+                rp0 += T::RWP;
+                int d1 = (int)rp0[2] - (int)rp0[0], s1 = 3 * ((int)rp0[0] + (int)rp0[2]) + 10 * (int)rp0[1];
+                const bool col_ok = inside || (ipx + i >= 0 && ipx + i < W);
 #pragma unroll 4
-            for (int idx = lane; idx < T::DW * T::DH; idx += 32) {
-                int j = idx / T::DW, i = idx - j * T::DW;
-                const unsigned char *r0 = raw + j * T::RWP + i, *r1 = r0 + T::RWP, *r2 = r1 + T::RWP;
-                int a0 = r0[0], a1 = r0[1], a2 = r0[2], b0 = r1[0], b2 = r1[2], c0 = r2[0], c1 = r2[1], c2 = r2[2];
-                int ix = 3 * (a2 - a0 + c2 - c0) + 10 * (b2 - b0);
-                int iy = 3 * (c0 - a0 + c2 - a2) + 10 * (c1 - a1);
-                if (!inside) {
-                    int qx = ipx + i, qy = ipy + j;
-                    if (qx < 0 || qx >= W || qy < 0 || qy >= H) { ix = 0; iy = 0; }
+                for (int j = j0; j < j1; j++) {
+                    rp0 += T::RWP;
+                    const int a = rp0[0], bb = rp0[1], c = rp0[2];
+                    const int d2 = c - a, s2 = 3 * (a + c) + 10 * bb;
+                    int ix = 3 * (d0 + d2) + 10 * d1, iy = s2 - s0;
+                    if (!(col_ok && (inside || (ipy + j >= 0 && ipy + j < H)))) { ix = 0; iy = 0; }
+                    der[j * T::DWP + i] = make_short2((short)ix, (short)iy);
+                    d0 = d1; d1 = d2; s0 = s1; s1 = s2;
                 }
-                der[j * T::DWP + i] = make_short2((short)ix, (short)iy);
             }
         }
         __syncwarp();
@@ -429,7 +467,7 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
         int a11 = 0, a12 = 0, a22 = 0;
 #pragma unroll
         for (int k = 0; k < T::RPL; k++) {
-            const unsigned char *r0 = raw + (run_y[k] + 1) * T::RWP + run_x[k] + 1, *r1 = r0 + T::RWP;
+            const unsigned char *r0 = raw + (run_y[k] + 1) * T::RWP + ro + run_x[k] + 1, *r1 = r0 + T::RWP;
             const short2 *d0 = der + run_y[k] * T::DWP + run_x[k], *d1 = d0 + T::DWP;
             int i00 = r0[0], i10 = r1[0];
             short2 e00 = d0[0], e10 = d1[0];
@@ -534,7 +572,7 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
 template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, int MINB>
 int launch_lk_t(const LKLevels &lv, int n_levels, int max_count, double eps, const lkf_lk_params *p, const float *prev_pts,
                 const int32_t *pt_counts, int max_pts, float *next_pts, uint8_t *status, float *err, int32_t *iters,
-                unsigned al4_mask, int B, cudaStream_t s)
+                unsigned al4_mask, unsigned ial4_mask, int B, cudaStream_t s)
 {
     using T = LKT<WW, WH, RUN, MARGIN, DWP_, TWC_>;
     constexpr size_t smem = (size_t)T::PER_WARP * LKT_WARPS;
@@ -547,7 +585,7 @@ int launch_lk_t(const LKLevels &lv, int n_levels, int max_count, double eps, con
     dim3 grid((max_pts + LKT_WARPS - 1) / LKT_WARPS, B);
     k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB><<<grid, LKT_WARPS * 32, smem, s>>>(
         lv, n_levels, max_count, eps, p->flags, p->min_eig_threshold, prev_pts, pt_counts, max_pts, next_pts, status, err, iters,
-        al4_mask);
+        al4_mask, ial4_mask);
     return LKF_OK;
 }
 
@@ -597,16 +635,18 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     const int area = p->win_w * p->win_h;
     dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, B);
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned al4_mask = 0;
-    for (int l = 0; l < n_levels; l++)
+    unsigned al4_mask = 0, ial4_mask = 0;
+    for (int l = 0; l < n_levels; l++) {
         if (aligned_to(&next_pyr[l], 4)) al4_mask |= 1u << l;
+        if (aligned_to(&prev_pyr[l], 4)) ial4_mask |= 1u << l;
+    }
     int rc = 1;
     if (p->win_w == 21 && p->win_h == 21)
-        rc = launch_lk_t<21, 21, 7, 6, 22, 52, 5>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, B, s);
+        rc = launch_lk_t<21, 21, 7, 6, 22, 52, 10>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 15 && p->win_h == 15)
-        rc = launch_lk_t<15, 15, 5, 6, 17, 36, 6>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, B, s);
+        rc = launch_lk_t<15, 15, 5, 6, 17, 36, 12>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 31 && p->win_h == 31)
-        rc = launch_lk_t<31, 31, 31, 6, 33, 52, 3>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, B, s);
+        rc = launch_lk_t<31, 31, 31, 6, 33, 52, 6>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     if (rc < 0) return rc;
     if (rc == LKF_OK) { LKF_LAUNCH_CHECK(ctx); return LKF_OK; }
     if (area <= 2048) {      // int32 lane partials cannot overflow (<= 64 px/lane * 8160*4080)
