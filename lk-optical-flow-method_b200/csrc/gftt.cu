@@ -93,6 +93,250 @@ k_min_eigen(const uint8_t *__restrict__ src, long long rp, long long ip, int H, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// a5, streaming form for odd block sizes 3/5/7 on 4-byte aligned rows with W % 4 == 0 (860, 1920, 3840 ...): same
+// arithmetic as k_min_eigen, but every value is computed once and nothing is staged through CTA-wide barriers.
+//   * A WARP owns 120 output columns (lanes 1..30, 4 columns each; lanes 0 and 31 carry the 3-column halo) and
+//     slides down a strip of rows.  Per image row a lane loads one aligned 32-bit word, gets the two neighbour
+//     bytes by shuffle, keeps the Sobel row terms of the last two rows in registers and forms the three float32
+//     products of its 4 columns (cv2's op order, explicitly rounded intrinsics).
+//   * Horizontal box sums: neighbour products by shuffle, FP64 sliding sum over the lane's 4 columns.
+//   * Vertical box sums: FP64 running sum V += H(y+R) - H(y-R-1); the last 8 rows of H live in a per-lane ring in
+//     shared memory (a lane only ever touches its own slots: no barrier).  Every term is a float32 product, so
+//     the FP64 sums are exact and order-free (7x7 terms span < 2^53 except for ulp-residue products, see A.4).
+//   * Borders: a product outside the image is the product AT the mirrored pixel (see k_min_eigen): in x the edge
+//     lanes mirror their own columns, in y the ring is addressed with the mirrored row.
+// ---------------------------------------------------------------------------------------------
+constexpr int MES_WARPS = 2, MES_COLS = 120, MES_PF = 3;
+template <int BS> struct MES {
+    static constexpr int R = BS / 2, RING = 2 * R + 1;
+    static constexpr size_t SMEM_PER_WARP = (size_t)RING * 3 * 128 * sizeof(double);
+    static constexpr size_t SMEM = MES_WARPS * SMEM_PER_WARP;
+};
+
+__device__ __forceinline__ float u8f(unsigned word, unsigned sel)
+{   // exact u8 -> f32: 0x4B0000vv is 8388608 + vv
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.0f;
+}
+__device__ __forceinline__ double shfl_up_d(double v)
+{
+    return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), 1), __shfl_up_sync(0xffffffffu, __double2loint(v), 1));
+}
+__device__ __forceinline__ double shfl_down_d(double v)
+{
+    return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(v), 1), __shfl_down_sync(0xffffffffu, __double2loint(v), 1));
+}
+
+// EDGE: the warp holds the first and/or last column group of the image (mirror selects needed); interior warps skip them
+template <int BS, bool EDGE>
+__device__ __forceinline__ void
+mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp, long long ip, int H, int W, float *__restrict__ dst,
+         long long drp, long long dip, int tail_cols, float s, float s2, int rows_per_strip, int dst_al16, int wx0)
+{
+    constexpr int R = MES<BS>::R, RING = MES<BS>::RING;
+    const int b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cx = wx0 - 4 + 4 * lane;                      // first of this lane's 4 columns
+    const bool valid = cx >= 0 && cx < W;
+    const bool first = EDGE && cx == 0, last = EDGE && cx == W - 4;
+    const bool emit = valid && lane >= 1 && lane <= 30;
+    // ring[slot][ch][half][lane]: a lane's two 16-byte halves sit in two lane-contiguous planes (conflict-free 128-bit access)
+    double *ring = reinterpret_cast<double *>(mes_smem + (size_t)warp * MES<BS>::SMEM_PER_WARP) + 2 * lane;
+    const uint8_t *img = src + (long long)b * ip + (valid ? cx : 0);
+    const int y0 = blockIdx.y * rows_per_strip, y1 = min(H, y0 + rows_per_strip);
+    bool tl[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) tl[j] = cx + j >= W - tail_cols;
+    const bool any_tail = tail_cols > 0;
+
+    auto load_word = [&](int y) -> uint32_t {               // y: any row index, mirrored here
+        return valid ? __ldg(reinterpret_cast<const uint32_t *>(img + (long long)reflect101(y, H) * rp)) : 0u;
+    };
+    // Sobel row terms of one image row for the lane's 4 columns: rd = I[x+1]-I[x-1] (exact), rs = [1 2 1] smoothing * s
+    auto row_terms = [&](uint32_t w, float (&rd)[4], float (&rs)[4]) {
+        const uint32_t wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
+        float f[6];
+        f[0] = first ? u8f(w, 0x7651) : u8f(wl, 0x7653);    // column -1 -> 1
+        f[1] = u8f(w, 0x7650); f[2] = u8f(w, 0x7651); f[3] = u8f(w, 0x7652); f[4] = u8f(w, 0x7653);
+        f[5] = last ? u8f(w, 0x7652) : u8f(wr, 0x7650);     // column W -> W-2
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            rd[j] = __fsub_rn(f[j + 2], f[j]);
+            rs[j] = __fmaf_rn(s, f[j + 2], __fmaf_rn(s2, f[j + 1], __fmul_rn(s, f[j])));
+            if (any_tail && tl[j])
+                rs[j] = __fadd_rn(__fadd_rn(__fmul_rn(s, f[j]), __fmul_rn(s2, f[j + 1])), __fmul_rn(s, f[j + 2]));
+        }
+    };
+    // horizontal FP64 box sums of one float32 product plane row (the lane's 4 columns)
+    auto hbox = [&](const float (&p)[4], double (&h)[4]) {
+        double v[10];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[3 + j] = (double)p[j];
+#pragma unroll
+        for (int k = 1; k <= R; k++) {
+            const double l = shfl_up_d(v[3 + 4 - k]);          // column -k   (left lane's column 4-k)
+            const double r = shfl_down_d(v[3 + k - 1]);        // column 3+k  (right lane's column k-1)
+            v[3 - k] = first ? v[3 + k] : l;                   // column -k -> k
+            v[6 + k] = last ? v[3 + 3 - k] : r;                // column W-1+k -> W-1-k
+        }
+        double acc = v[3 - R];
+#pragma unroll
+        for (int k = 4 - R; k <= 3 + R; k++) acc = __dadd_rn(acc, v[k]);
+        h[0] = acc;
+#pragma unroll
+        for (int j = 1; j < 4; j++) {
+            acc = __dsub_rn(__dadd_rn(acc, v[3 + R + j]), v[2 - R + j]);
+            h[j] = acc;
+        }
+    };
+    auto ring_ld = [&](int row, int ch, double (&h)[4]) {
+        const double2 *q = reinterpret_cast<const double2 *>(ring + ((size_t)(row % RING) * 3 + ch) * 128);
+        const double2 a = q[0], c = q[32];
+        h[0] = a.x; h[1] = a.y; h[2] = c.x; h[3] = c.y;
+    };
+    auto ring_st = [&](int row, int ch, const double (&h)[4]) {
+        double2 *q = reinterpret_cast<double2 *>(ring + ((size_t)(row % RING) * 3 + ch) * 128);
+        q[0] = make_double2(h[0], h[1]); q[32] = make_double2(h[2], h[3]);
+    };
+    auto emit_row = [&](int y, const double (&vxx)[4], const double (&vxy)[4], const double (&vyy)[4]) {
+        if (!emit) return;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float a = __fmul_rn((float)vxx[j], 0.5f), bb = (float)vxy[j], c2 = __fmul_rn((float)vyy[j], 0.5f);
+            const float t = __fsub_rn(a, c2);
+            o[j] = __fsub_rn(__fadd_rn(a, c2), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(bb, bb))));
+        }
+        float *q = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(dst) + (long long)b * dip + (long long)y * drp) + cx;
+        if (dst_al16) __stcs(reinterpret_cast<float4 *>(q), make_float4(o[0], o[1], o[2], o[3]));
+        else { q[0] = o[0]; q[1] = o[1]; q[2] = o[2]; q[3] = o[3]; }
+    };
+
+    // product rows ylo..yhi are computed in order; image rows ylo-1 .. yhi+1 (mirrored) feed them, prefetched MES_PF ahead
+    const int ylo = max(0, y0 - R), yhi = min(H - 1, y1 - 1 + R);
+    float rd_m[4], rs_m[4], rd_c[4], rs_c[4];
+    row_terms(load_word(ylo - 1), rd_m, rs_m);
+    row_terms(load_word(ylo), rd_c, rs_c);
+    uint32_t pf[MES_PF];
+#pragma unroll
+    for (int k = 0; k < MES_PF; k++) pf[k] = load_word(min(ylo + 1 + k, yhi + 1));
+
+    double vxx[4], vxy[4], vyy[4];
+    bool have_v = false;
+    int ynext = y0;
+    // V of output row y: first time the direct (mirrored) window sum from the ring, afterwards + entering - leaving row
+    auto advance = [&](int y, const double (&nxx)[4], const double (&nxy)[4], const double (&nyy)[4],
+                       const double (&oxx)[4], const double (&oxy)[4], const double (&oyy)[4]) {
+        if (!have_v) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { vxx[j] = 0.0; vxy[j] = 0.0; vyy[j] = 0.0; }
+#pragma unroll
+            for (int k = -R; k <= R; k++) {
+                double hxx[4], hxy[4], hyy[4];
+                const int row = reflect101(y + k, H);
+                ring_ld(row, 0, hxx); ring_ld(row, 1, hxy); ring_ld(row, 2, hyy);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    vxx[j] = __dadd_rn(vxx[j], hxx[j]); vxy[j] = __dadd_rn(vxy[j], hxy[j]); vyy[j] = __dadd_rn(vyy[j], hyy[j]);
+                }
+            }
+            have_v = true;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                vxx[j] = __dsub_rn(__dadd_rn(vxx[j], nxx[j]), oxx[j]);
+                vxy[j] = __dsub_rn(__dadd_rn(vxy[j], nxy[j]), oxy[j]);
+                vyy[j] = __dsub_rn(__dadd_rn(vyy[j], nyy[j]), oyy[j]);
+            }
+        }
+        emit_row(y, vxx, vxy, vyy);
+    };
+
+#pragma unroll 1
+    for (int r = ylo; r <= yhi; r++) {
+        const uint32_t w = pf[0];
+#pragma unroll
+        for (int k = 0; k + 1 < MES_PF; k++) pf[k] = pf[k + 1];
+        pf[MES_PF - 1] = load_word(min(r + 1 + MES_PF, yhi + 1));
+        float rd_p[4], rs_p[4];
+        row_terms(w, rd_p, rs_p);
+        float pxx[4], pxy[4], pyy[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float dx = __fmaf_rn(s, __fadd_rn(rd_m[j], rd_p[j]), __fmul_rn(s2, rd_c[j]));
+            const float dy = __fsub_rn(rs_p[j], rs_m[j]);
+            pxx[j] = __fmul_rn(dx, dx); pxy[j] = __fmul_rn(dx, dy); pyy[j] = __fmul_rn(dy, dy);
+            rd_m[j] = rd_c[j]; rd_c[j] = rd_p[j]; rs_m[j] = rs_c[j]; rs_c[j] = rs_p[j];
+        }
+        double hxx[4], hxy[4], hyy[4], oxx[4], oxy[4], oyy[4];
+        hbox(pxx, hxx); hbox(pxy, hxy); hbox(pyy, hyy);
+        const bool out = r - R == ynext;                    // warp-uniform
+        if (out && have_v) {                                // leaving row: read before its slot is overwritten (RING = 2R+1)
+            const int ro = reflect101(ynext - R - 1, H);
+            ring_ld(ro, 0, oxx); ring_ld(ro, 1, oxy); ring_ld(ro, 2, oyy);
+        }
+        ring_st(r, 0, hxx); ring_st(r, 1, hxy); ring_st(r, 2, hyy);
+        if (out) { advance(ynext, hxx, hxy, hyy, oxx, oxy, oyy); ynext++; }
+    }
+    // bottom of the image: the entering rows are mirrored rows that are still in the ring
+    while (ynext < y1) {
+        double hxx[4], hxy[4], hyy[4], oxx[4], oxy[4], oyy[4];
+        if (have_v) {
+            const int rn = reflect101(ynext + R, H), ro = reflect101(ynext - R - 1, H);
+            ring_ld(rn, 0, hxx); ring_ld(rn, 1, hxy); ring_ld(rn, 2, hyy);
+            ring_ld(ro, 0, oxx); ring_ld(ro, 1, oxy); ring_ld(ro, 2, oyy);
+        }
+        advance(ynext, hxx, hxy, hyy, oxx, oxy, oyy);
+        ynext++;
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(MES_WARPS * 32)
+k_min_eigen_stream(const uint8_t *__restrict__ src, long long rp, long long ip, int H, int W, float *__restrict__ dst,
+                   long long drp, long long dip, int tail_cols, float s, float s2, int rows_per_strip, int dst_al16,
+                   const int32_t *__restrict__ enable)
+{
+    extern __shared__ __align__(16) unsigned char mes_smem[];
+    if (enable && !enable[blockIdx.z]) return;
+    const int wx0 = (blockIdx.x * MES_WARPS + (threadIdx.x >> 5)) * MES_COLS;
+    if (wx0 >= W) return;                                   // warp-uniform; the kernel has no CTA-wide barrier
+    if (wx0 == 0 || wx0 + MES_COLS + 4 >= W)
+        mes_body<BS, true>(mes_smem, src, rp, ip, H, W, dst, drp, dip, tail_cols, s, s2, rows_per_strip, dst_al16, wx0);
+    else
+        mes_body<BS, false>(mes_smem, src, rp, ip, H, W, dst, drp, dip, tail_cols, s, s2, rows_per_strip, dst_al16, wx0);
+}
+
+template <int BS>
+int launch_min_eigen_stream(lkf_ctx *ctx, const lkf_image *src, const lkf_image *eig, int tail, float s, float s2,
+                            const int32_t *enable, cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) {
+        LKF_CUDA(cudaFuncSetAttribute(k_min_eigen_stream<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MES<BS>::SMEM));
+        LKF_CUDA(cudaFuncSetAttribute(k_min_eigen_stream<BS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr = true;
+    }
+    const int W = src->width, H = src->height, B = src->batch;
+    const int warps_x = (W + MES_COLS - 1) / MES_COLS, ctas_x = (warps_x + MES_WARPS - 1) / MES_WARPS;
+    // strip height: fill whole waves of resident CTAs (shared memory bounds residency), 8..64 rows per strip
+    const int sms = ctx ? ctx->sm_count : 148;
+    int per_sm = (int)((227 * 1024) / (MES<BS>::SMEM + 1024));
+    per_sm = per_sm > 6 ? 6 : per_sm;                         // ~160 registers x 64 threads: 6 CTAs
+    const long long cap = (long long)sms * per_sm, col_ctas = (long long)ctas_x * B;
+    const long long min_ctas = col_ctas * ((H + 63) / 64);
+    const long long waves = (min_ctas + cap - 1) / cap;
+    long long strips = waves * cap / col_ctas;
+    if (strips < 1) strips = 1;
+    int rows = (int)((H + strips - 1) / strips);
+    rows = rows < 8 ? 8 : (rows > 64 ? 64 : rows);
+    dim3 grid(ctas_x, (H + rows - 1) / rows, B);
+    k_min_eigen_stream<BS><<<grid, MES_WARPS * 32, MES<BS>::SMEM, st>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch, H, W,
+                                                                        (float *)eig->data, eig->row_pitch, eig->image_pitch, tail, s, s2,
+                                                                        rows, aligned_to(eig, 16) ? 1 : 0, enable);
+    return LKF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // a6 helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned f2key(float f)
@@ -324,7 +568,7 @@ k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__
 
 }  // namespace
 
-static int min_eigen_impl(const lkf_image *src, const lkf_image *eig, int block_size, int dy_tail_cols, const int32_t *enable,
+static int min_eigen_impl(lkf_ctx *ctx, const lkf_image *src, const lkf_image *eig, int block_size, int dy_tail_cols, const int32_t *enable,
                           lkf_stream stream)
 {
     if (!img_ok(src, 1, 1) || !img_ok(eig, 1, 4) || src->batch != eig->batch || src->height != eig->height ||
@@ -336,6 +580,15 @@ static int min_eigen_impl(const lkf_image *src, const lkf_image *eig, int block_
     if (dy_tail_cols < 0) dy_tail_cols = W % 32;
     const double scale = 1.0 / (4.0 * bs * 255.0);           // (1 << (ksize-1)) * blockSize * 255, ksize = 3
     const float s = (float)scale, s2 = (float)(2.0 * scale);
+    if ((bs == 3 || bs == 5 || bs == 7) && W % 4 == 0 && W >= 8 && H >= 8 && aligned_to(src, 4)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        int rc = bs == 3 ? launch_min_eigen_stream<3>(ctx, src, eig, dy_tail_cols, s, s2, enable, st)
+               : bs == 5 ? launch_min_eigen_stream<5>(ctx, src, eig, dy_tail_cols, s, s2, enable, st)
+                         : launch_min_eigen_stream<7>(ctx, src, eig, dy_tail_cols, s, s2, enable, st);
+        if (rc != LKF_OK) return rc;
+        LKF_LAUNCH_CHECK(nullptr);
+        return LKF_OK;
+    }
     const int pw = ME_W + bs - 1, ph = ME_H + bs - 1, uw = pw + 2, uh = ph + 2, uws = (uw + 3) & ~3;
     size_t smem = (size_t)3 * ph * ME_W * 8 + (size_t)3 * ph * pw * 4 + (size_t)uh * uws;
     if (smem > 48 * 1024) LKF_CUDA(cudaFuncSetAttribute(k_min_eigen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -350,7 +603,7 @@ static int min_eigen_impl(const lkf_image *src, const lkf_image *eig, int block_
 LKF_EXPORT int lkf_corner_min_eigen_f32(const lkf_image *src, const lkf_image *eig, int block_size, int dy_tail_cols,
                                         lkf_stream stream)
 {
-    return min_eigen_impl(src, eig, block_size, dy_tail_cols, nullptr, stream);
+    return min_eigen_impl(nullptr, src, eig, block_size, dy_tail_cols, nullptr, stream);
 }
 
 static int gftt_select_impl(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *eig, const lkf_image *mask,
@@ -435,7 +688,7 @@ LKF_EXPORT int lkf_gftt_detect(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf
     int rc = lkf_scratch(ctx, 3, pitch * src->height * src->batch, &eigbuf);
     if (rc != LKF_OK) return rc;
     lkf_image eig = {eigbuf, src->batch, src->height, src->width, 1, (int64_t)pitch, (int64_t)(pitch * src->height)};
-    if ((rc = min_eigen_impl(src, &eig, p->block_size, p->dy_tail_cols, image_enable, stream)) != LKF_OK) return rc;
+    if ((rc = min_eigen_impl(ctx, src, &eig, p->block_size, p->dy_tail_cols, image_enable, stream)) != LKF_OK) return rc;
     lkf_count_launch(ctx);
     return gftt_select_impl(ctx, p, &eig, mask, n_masks, image_enable, corners, counts, max_out, stream);
 }

@@ -37,6 +37,13 @@ timeit(lambda: ops.gaussian_blur3(gray, out=g2), B * 2 * P, "blur3 (a2)")
 timeit(lambda: ops.pyr_down(gray, out=l1), B * 1.25 * P, "pyrdown L0->L1")
 timeit(lambda: ops.pyr_down(l1, out=l2), B * 1.25 * P / 4, "pyrdown L1->L2")
 timeit(lambda: ops.min_eigen(gray[:4], 7, out=eig), 4 * 5 * P, "min_eigen bs7 (4 img)")
+eig1 = ops.min_eigen(gray[:1], 7)
+timeit(lambda: ops.min_eigen(gray[:1], 7, out=eig1), 1 * 5 * P, "min_eigen bs7 (1 img)")
+eig32 = ops.min_eigen(gray, 7)
+timeit(lambda: ops.min_eigen(gray, 7, out=eig32), B * 5 * P, "min_eigen bs7 (32 img)")
+eig3 = ops.min_eigen(gray, 3)
+timeit(lambda: ops.min_eigen(gray, 3, out=eig3), B * 5 * P, "min_eigen bs3 (32 img)")
+del eig32, eig3
 sch = ops.scharr(gray[:8])
 timeit(lambda: ops.scharr(gray[:8], out=sch), 8 * 5 * P, "scharr (8 img)")
 a = torch.empty(256 << 20, dtype=torch.uint8, device="cuda"); b = torch.empty_like(a)

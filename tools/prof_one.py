@@ -1,0 +1,27 @@
+"""Run one operator a few times (for `ncu -k <kernel>` captures).  Usage: prof_one.py <op> [B]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from lk_optical_flow_method_b200 import ops, synth
+
+op = sys.argv[1]
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+H, W = 1080, 1920
+tex = torch.from_numpy(synth.make_texture(W, H, 0)).cuda()
+frames = torch.stack([synth.zoom_frame(tex, W, H, t) for t in range(B)])
+gray = ops.process_img(frames)
+if op == "min_eigen":
+    for _ in range(3):
+        e = ops.min_eigen(gray, 7)
+elif op == "gftt":
+    e = ops.min_eigen(gray, 7)
+    for _ in range(3):
+        ops.gftt_select(e, None, 2000, 0.01, 7, 2000)
+elif op == "process_img":
+    for _ in range(3):
+        ops.process_img(frames, out=gray)
+elif op == "pyrdown":
+    for _ in range(3):
+        l1 = ops.pyr_down(gray)
+torch.cuda.synchronize()
+print("done", op)
