@@ -262,7 +262,7 @@ constexpr int LKT_WARPS = 2;     // small CTAs: a CTA retires when its slowest f
 
 template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_>
 struct LKT {
-    static constexpr int AREA = WW * WH;
+    static constexpr int AREA = WW * WH, WW_ = WW, WH_ = WH;
     static constexpr int RPR = WW / RUN;                 // runs per window row
     static constexpr int NRUNS = RPR * WH;
     static constexpr int RPL = (NRUNS + 31) / 32;        // runs per lane
@@ -275,15 +275,67 @@ struct LKT {
     static constexpr int DW = WW + 1, DH = WH + 1, DWP = DWP_;      // DWP: der pitch (words), chosen bank-conflict-poor
     static constexpr int TWC = TWC_;                                  // tile pitch (bytes), multiple of 4
     static constexpr int TH = WH + 1 + 2 * MARGIN;
-    static constexpr int DER_BYTES = (DWP * DH * 4 + 15) & ~15, TILE_BYTES = (TWC * TH + 15) & ~15;
-    static constexpr int RAW_BYTES = (RWP * RH + 15) & ~15;
-    static constexpr int PER_WARP = DER_BYTES + TILE_BYTES + RAW_BYTES;
+    // interior windows: U = Q14-weighted raw sums on the (WW+2)x(WH+2) grid, int32, pitch UP (bank-spread, 16-byte rows)
+    static constexpr int USEG = (WW + 2 + 3) / 4, UP = 4 * USEG + ((4 * USEG) % 8 == 0 ? 4 : 0), UH = WH + 2;
+    static constexpr int DER_ONLY = (DWP * DH * 4 + 15) & ~15, U_BYTES = (UP * UH * 4 + 15) & ~15;
+    static constexpr int DER_BYTES = DER_ONLY > U_BYTES ? DER_ONLY : U_BYTES, TILE_BYTES = (TWC * TH + 15) & ~15;
+    static constexpr int RAW_BYTES = ((RWP * RH + 15) & ~15) + 16;     // + slack: word loaders read up to 2 words past a run
+    static constexpr int BRD_I_BYTES = (AREA * 2 + 15) & ~15, BRD_BYTES = BRD_I_BYTES + ((AREA * 4 + 15) & ~15);   // border template hand-over
+    static constexpr int PER_WARP = DER_BYTES + TILE_BYTES + 2 * RAW_BYTES + BRD_BYTES;      // raw is double-buffered
     static_assert(WW % RUN == 0, "RUN must divide the window width");
     static_assert(AREA <= 2048, "int32 lane partials");
     static_assert(TWC % 4 == 0 && TWC >= WW + 1 + 2 * MARGIN + 3, "tile pitch");
     static_assert(DWP >= DW, "der pitch");
     static_assert(RWW <= 16 && TILE_WPR <= 32, "loader lane mapping");
 };
+
+// two-way dot product: signed 16-bit halves of `a` (Q14 weights, -1..16384) times unsigned bytes 0,1 (lo) / 2,3 (hi) of `b`
+__device__ __forceinline__ int dp2a_lo(int a, unsigned b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(int a, unsigned b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// Q14 bilinear samples of RUN consecutive pixels whose top-left samples start at byte `col` of the 4-byte aligned
+// rows r0 (upper) and r1 (lower): v[t] = (r0[col+t] w00 + r0[col+t+1] w01 + r1[col+t] w10 + r1[col+t+1] w11 + 2^8) >> 9.
+// Rows are read as aligned 32-bit words and realigned with funnel shifts; each pixel then costs two DP2A (the byte
+// pair (t, t+1) is the low or high half of the aligned word or of the word shifted by one byte).
+// DESCALE = false returns the raw Q14 sums (no rounding, no shift).
+template <int RUN, bool DESCALE = true>
+__device__ __forceinline__ void bilinear_run(const unsigned char *r0, const unsigned char *r1, int col, int wT, int wB, int (&v)[RUN])
+{
+    constexpr int NA = (RUN + 1 + 3) / 4;
+    const uint32_t *q0 = reinterpret_cast<const uint32_t *>(r0) + (col >> 2);
+    const uint32_t *q1 = reinterpret_cast<const uint32_t *>(r1) + (col >> 2);
+    const int sh = (col & 3) * 8;
+    uint32_t a[NA + 1], c[NA + 1];
+#pragma unroll
+    for (int i = 0; i <= NA; i++) { a[i] = q0[i]; c[i] = q1[i]; }
+#pragma unroll
+    for (int i = 0; i < NA; i++) { a[i] = __funnelshift_r(a[i], a[i + 1], sh); c[i] = __funnelshift_r(c[i], c[i + 1], sh); }
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+        const uint32_t a1 = i + 1 < NA ? __funnelshift_r(a[i], a[i + 1], 8) : a[i] >> 8;
+        const uint32_t c1 = i + 1 < NA ? __funnelshift_r(c[i], c[i + 1], 8) : c[i] >> 8;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int t = 4 * i + j;
+            if (t < RUN) {
+                const uint32_t wa = (j & 1) ? a1 : a[i], wc = (j & 1) ? c1 : c[i];
+                int acc = (j & 2) ? dp2a_hi(wT, wa, DESCALE ? 256 : 0) : dp2a_lo(wT, wa, DESCALE ? 256 : 0);
+                acc = (j & 2) ? dp2a_hi(wB, wc, acc) : dp2a_lo(wB, wc, acc);
+                v[t] = DESCALE ? acc >> 9 : acc;
+            }
+        }
+    }
+}
 
 // tile origin: window + MARGIN, x aligned down to 4; slid back inside the level when the window itself is inside
 // (keeps the aligned 32-bit fast path for features near the border)
@@ -300,63 +352,126 @@ __device__ __forceinline__ void place_tile(int ix, int iy, int W, int H, int &tx
     if (iy >= 0 && iy + WH1 <= H && H >= T::TH) ty0 = min(max(ty0, 0), H - T::TH);
 }
 
-// `next` tile: TILE_LPR lanes per row (TILE_WPR of them load one aligned 32-bit word), 32/TILE_LPR rows per pass;
-// all loads of the tile are issued before the first store (one memory round trip instead of one per pass).
+// Loads NROWS x NWORDS 32-bit words (rows gy0.., columns from the 4-aligned gx0) of a 4-byte aligned plane into `dst`
+// (pitch NWORDS words): LPR lanes per row, 32/LPR rows per pass, all loads issued before the first store (one memory
+// round trip).  Rows outside the level are mirrored (REFLECT_101); a word that straddles the left/right border is
+// assembled from mirrored bytes -- so windows near the border keep the aligned path.
+template <int NROWS, int NWORDS, int LPR>
+__device__ __noinline__ void load_words_edge(const uint8_t *__restrict__ P, long long rp, int W, int H, int gx0, int gy0,
+                                              uint32_t *dst, int lane)
+{   // cold path (window near the border of the level): rolled loops, one word per lane and pass
+    constexpr int RPP = 32 / LPR;
+    const int k = lane & (LPR - 1), r0 = lane / LPR, gx = gx0 + 4 * k;
+    if (k >= NWORDS) return;
+    const bool word_ok = gx >= 0 && gx + 3 < W;
+    const int x0 = reflect101(gx, W), x1 = reflect101(gx + 1, W), x2 = reflect101(gx + 2, W), x3 = reflect101(gx + 3, W);
+#pragma unroll 1
+    for (int r = r0; r < NROWS; r += RPP) {
+        const uint8_t *row = P + (long long)reflect101(gy0 + r, H) * rp;
+        uint32_t v;
+        if (word_ok) v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+        else v = (uint32_t)row[x0] | ((uint32_t)row[x1] << 8) | ((uint32_t)row[x2] << 16) | ((uint32_t)row[x3] << 24);
+        dst[r * NWORDS + k] = v;
+    }
+}
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ASYNCHRONOUS: the interior path issues cp.async copies (global -> shared, no registers, no stall); the caller commits
+// the group and waits (cp_async_wait + __syncwarp) before reading.  The cold border path loads synchronously.
+template <int NROWS, int NWORDS, int LPR>
+__device__ __forceinline__ void load_words(const uint8_t *__restrict__ P, long long rp, int W, int H, int gx0, int gy0,
+                                           uint32_t *dst, int lane)
+{
+    if (gx0 >= 0 && gy0 >= 0 && gx0 + 4 * NWORDS <= W && gy0 + NROWS <= H) {        // warp-uniform
+        constexpr int RPP = 32 / LPR, NP = (NROWS + RPP - 1) / RPP;
+        const int k = lane & (LPR - 1), r0 = lane / LPR, gx = gx0 + 4 * k;
+        if (k < NWORDS) {
+            const uint8_t *src = P + (long long)(gy0 + r0) * rp + gx;
+            uint32_t *t = dst + r0 * NWORDS + k;
+#pragma unroll
+            for (int q = 0; q < NP; q++)
+                if (r0 + q * RPP < NROWS) cp_async4(t + q * RPP * NWORDS, src + (long long)q * RPP * rp);
+        }
+    } else {
+        load_words_edge<NROWS, NWORDS, LPR>(P, rp, W, H, gx0, gy0, dst, lane);
+    }
+}
+
+template <int NROWS, int PITCH>
+__device__ __noinline__ void load_bytes_unaligned(const uint8_t *__restrict__ P, long long rp, int W, int H, int gx0, int gy0,
+                                                  int ncols, unsigned char *dst, int lane)
+{   // cold path: plane not 4-byte aligned.  A lane owns columns (reflect once per column), rows in the inner loop
+#pragma unroll 1
+    for (int c = lane; c < ncols; c += 32) {
+        const uint8_t *col = P + reflect101(gx0 + c, W);
+#pragma unroll 1
+        for (int r = 0; r < NROWS; r++) dst[r * PITCH + c] = col[(long long)reflect101(gy0 + r, H) * rp];
+    }
+}
+
+// `next` tile around (tx0, ty0)
 template <class T>
 __device__ __forceinline__ void load_j_tile(const uint8_t *__restrict__ J, long long rp, int W, int H, bool al4,
                                             int tx0, int ty0, unsigned char *tile, int lane)
 {
-    const bool inside = tx0 >= 0 && ty0 >= 0 && tx0 + T::TWC <= W && ty0 + T::TH <= H;
-    if (inside && al4) {
-        constexpr int RPP = 32 / T::TILE_LPR, NP = (T::TH + RPP - 1) / RPP;
-        const int k = lane & (T::TILE_LPR - 1), r0 = lane / T::TILE_LPR;
-        const uint32_t *base = reinterpret_cast<const uint32_t *>(J + (long long)(ty0 + r0) * rp + tx0) + k;
-        const long long step = (rp * RPP) >> 2;
-        uint32_t v[NP];
-#pragma unroll
-        for (int q = 0; q < NP; q++)
-            if (k < T::TILE_WPR && r0 + q * RPP < T::TH) v[q] = __ldg(base + q * step);
-        uint32_t *t = reinterpret_cast<uint32_t *>(tile) + r0 * T::TILE_WPR + k;
-#pragma unroll
-        for (int q = 0; q < NP; q++)
-            if (k < T::TILE_WPR && r0 + q * RPP < T::TH) t[q * RPP * T::TILE_WPR] = v[q];
+    if (al4) {
+        load_words<T::TH, T::TILE_WPR, T::TILE_LPR>(J, rp, W, H, tx0, ty0, reinterpret_cast<uint32_t *>(tile), lane);
     } else {
-        // mirrored path: a lane owns columns (reflect once per column), rows in the inner loop
-        for (int c = lane; c < T::TWC; c += 32) {
-            const uint8_t *col = J + reflect101(tx0 + c, W);
-            for (int r = 0; r < T::TH; r++) tile[r * T::TWC + c] = col[(long long)reflect101(ty0 + r, H) * rp];
-        }
+        load_bytes_unaligned<T::TH, T::TWC>(J, rp, W, H, tx0, ty0, T::TWC, tile, lane);
     }
 }
 
 // template neighbourhood: rows ipy-1 .. ipy+WH+1, columns from the 4-aligned ax <= ipx-1; returns the byte offset of
-// column ipx-1 inside a raw row (0..3 on the aligned path, 0 on the mirrored path)
+// column ipx-1 inside a raw row (0..3 on the aligned path, 0 on the unaligned path)
 template <class T>
 __device__ __forceinline__ int load_raw(const uint8_t *__restrict__ I, long long rp, int W, int H, bool al4, int ipx, int ipy,
                                         unsigned char *raw, int lane)
 {
-    const int ax = ((ipx - 1) >> 2) << 2;
-    const bool inside = al4 && ax >= 0 && ipy >= 1 && ax + T::RWP <= W && ipy + T::RH - 2 < H;
-    if (inside) {
-        constexpr int RPP = 32 / T::RAW_LPR, NP = (T::RH + RPP - 1) / RPP;
-        const int k = lane & (T::RAW_LPR - 1), r0 = lane / T::RAW_LPR;
-        const uint32_t *base = reinterpret_cast<const uint32_t *>(I + (long long)(ipy - 1 + r0) * rp + ax) + k;
-        const long long step = (rp * RPP) >> 2;
-        uint32_t v[NP];
-#pragma unroll
-        for (int q = 0; q < NP; q++)
-            if (k < T::RWW && r0 + q * RPP < T::RH) v[q] = __ldg(base + q * step);
-        uint32_t *t = reinterpret_cast<uint32_t *>(raw) + r0 * T::RWW + k;
-#pragma unroll
-        for (int q = 0; q < NP; q++)
-            if (k < T::RWW && r0 + q * RPP < T::RH) t[q * RPP * T::RWW] = v[q];
+    if (al4) {
+        const int ax = ((ipx - 1) >> 2) << 2;
+        load_words<T::RH, T::RWW, T::RAW_LPR>(I, rp, W, H, ax, ipy - 1, reinterpret_cast<uint32_t *>(raw), lane);
         return (ipx - 1) - ax;
     }
-    for (int c = lane; c < T::RW; c += 32) {
-        const uint8_t *col = I + reflect101(ipx - 1 + c, W);
-        for (int r = 0; r < T::RH; r++) raw[r * T::RWP + c] = col[(long long)reflect101(ipy - 1 + r, H) * rp];
-    }
+    load_bytes_unaligned<T::RH, T::RWP>(I, rp, W, H, ipx - 1, ipy - 1, T::RW, raw, lane);
     return 0;
+}
+
+// Template of a window that touches the border of the level: Scharr on the (WW+1)x(WH+1) sample grid with ZERO outside
+// the level, then the Q14 bilinear patch (I*32, Ix, Ix) for every window pixel -> shared memory (oI, oD).
+template <class T>
+__device__ __noinline__ void template_border(const unsigned char *raw, int ro, short2 *der, short *oI, short2 *oD, int ipx, int ipy,
+                                             int W, int H, int w00, int w01, int w10, int w11, int lane)
+{
+#pragma unroll 1
+    for (int idx = lane; idx < T::DW * T::DH; idx += 32) {
+        const int j = idx / T::DW, i = idx - j * T::DW;
+        const unsigned char *r0 = raw + j * T::RWP + ro + i, *r1 = r0 + T::RWP, *r2 = r1 + T::RWP;
+        const int qx = ipx + i, qy = ipy + j;
+        int ix = 0, iy = 0;
+        if (qx >= 0 && qx < W && qy >= 0 && qy < H) {
+            ix = 3 * (r0[2] - r0[0]) + 10 * (r1[2] - r1[0]) + 3 * (r2[2] - r2[0]);
+            iy = 3 * (r2[0] - r0[0]) + 10 * (r2[1] - r0[1]) + 3 * (r2[2] - r0[2]);
+        }
+        der[j * T::DWP + i] = make_short2((short)ix, (short)iy);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int idx = lane; idx < T::AREA; idx += 32) {
+        const int y = idx / T::WW_, x = idx - y * T::WW_;
+        const unsigned char *r0 = raw + (y + 1) * T::RWP + ro + x + 1, *r1 = r0 + T::RWP;
+        const short2 d00 = der[y * T::DWP + x], d01 = der[y * T::DWP + x + 1], d10 = der[(y + 1) * T::DWP + x],
+                     d11 = der[(y + 1) * T::DWP + x + 1];
+        oI[idx] = (short)descale(r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11, 9);
+        oD[idx] = make_short2((short)descale(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14),
+                              (short)descale(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14));
+    }
+    __syncwarp();
 }
 
 template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, int MINB>
@@ -376,7 +491,8 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
     unsigned char *uni = smem_all + (size_t)warp * T::PER_WARP;
     short2 *der = reinterpret_cast<short2 *>(uni);          // Scharr on the sample grid (setup phase)
     unsigned char *tile = uni + T::DER_BYTES;                // `next` tile (prefetched at level entry)
-    unsigned char *raw = tile + T::TILE_BYTES;
+    unsigned char *raw_buf = tile + T::TILE_BYTES;          // raw[l & 1]: template neighbourhood of level l (prefetched one level ahead)
+    unsigned char *brd = raw_buf + 2 * T::RAW_BYTES;
 
     // this lane's runs: (row, first column) -- compile-time count, runtime validity
     int run_y[T::RPL], run_x[T::RPL];
@@ -400,12 +516,29 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
     int iters = 0;
     const float FLT_SCALE = 1.f / (1 << 20);
 
+    // template neighbourhood of level l -> raw[l & 1]; its position depends only on prevPts, so it is fetched one level
+    // ahead (cp.async) and never waited for, except at the top level
+    auto issue_raw = [&](int l) {
+        const float sc = 1.f / (float)(1 << l);
+        const float px = __fsub_rn(__fmul_rn(ppx, sc), hx), py = __fsub_rn(__fmul_rn(ppy, sc), hy);
+        const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+        if (!out_of_level(px, py, ipx, ipy, WW, WH, lv.W[l], lv.H[l]))
+            load_raw<T>(lv.prev[l] + (long long)b * lv.pip[l], lv.prp[l], lv.W[l], lv.H[l], (ial4_mask >> l) & 1u, ipx, ipy,
+                        raw_buf + (l & 1) * T::RAW_BYTES, lane);
+        cp_async_commit();
+    };
+    issue_raw(n_levels - 1);
+    bool tile_pending = false;
+
     for (int l = n_levels - 1; l >= 0; --l) {
         const int W = lv.W[l], H = lv.H[l];
-        const uint8_t *I = lv.prev[l] + (long long)b * lv.pip[l];
         const uint8_t *J = lv.next[l] + (long long)b * lv.nip[l];
-        const long long irp = lv.prp[l], jrp = lv.nrp[l];
+        const long long jrp = lv.nrp[l];
         const bool jal4 = (al4_mask >> l) & 1u, ial4 = (ial4_mask >> l) & 1u;
+        unsigned char *raw = raw_buf + (l & 1) * T::RAW_BYTES;
+        if (tile_pending) { cp_async_wait<0>(); tile_pending = false; }     // a level left early: its tile copy must land first
+        __syncwarp();
+        if (l > 0) issue_raw(l - 1); else cp_async_commit();
         const float sc = 1.f / (float)(1 << l);
         float px = __fmul_rn(ppx, sc), py = __fmul_rn(ppy, sc);
         float nx, ny;
@@ -423,67 +556,87 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
         int w00, w01, w10, w11;
         weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
 
-        // prefetch the `next` tile around the entry estimate (independent of the template set-up below)
+        // prefetch the `next` tile around the entry estimate (asynchronous; awaited just before the first sweep)
         int tx0, ty0;
-        __syncwarp();
         {
             const float fx = __fsub_rn(nx, hx), fy = __fsub_rn(ny, hy);
             place_tile<T>(__float2int_rd(fx), __float2int_rd(fy), W, H, tx0, ty0);
             load_j_tile<T>(J, jrp, W, H, jal4, tx0, ty0, tile, lane);
+            cp_async_commit();
+            tile_pending = true;
         }
-        // 1. raw (WW+3)x(WH+3) neighbourhood of prev (aligned words, or mirrored bytes near the border)
-        const int ro = load_raw<T>(I, irp, W, H, ial4, ipx, ipy, raw, lane);
+        // 1. raw (WW+3)x(WH+3) neighbourhood of prev: issued one level ago; the two newest groups (next level's raw,
+        //    this level's tile) may still be in flight
+        const int ro = ial4 ? (ipx - 1) - (((ipx - 1) >> 2) << 2) : 0;
+        cp_async_wait<2>();
         __syncwarp();
-        // 2. Scharr on the (WW+1)x(WH+1) sample grid, zero outside the level.  A lane owns a column and slides down
-        //    the rows keeping the last two row terms: Ix = 3 dx(j) + 10 dx(j+1) + 3 dx(j+2), Iy = S(j+2) - S(j).
-        {
-            constexpr int G = T::DW <= 16 ? 2 : 1;                 // column groups that split the rows (narrow windows)
-            constexpr int LPG = 32 / G, RPG = (T::DH + G - 1) / G;
-            const int i = lane % LPG, grp = lane / LPG;
-            const int j0 = grp * RPG, j1 = min(T::DH, j0 + RPG);
-            const bool inside = ipx >= 0 && ipy >= 0 && ipx + WW < W && ipy + WH < H;
-            if (i < T::DW) {
-                const unsigned char *rp0 = raw + j0 * T::RWP + ro + i;
-                int d0 = (int)rp0[2] - (int)rp0[0], s0 = 3 * ((int)rp0[0] + (int)rp0[2]) + 10 * (int)rp0[1];
-                rp0 += T::RWP;
-                int d1 = (int)rp0[2] - (int)rp0[0], s1 = 3 * ((int)rp0[0] + (int)rp0[2]) + 10 * (int)rp0[1];
-                const bool col_ok = inside || (ipx + i >= 0 && ipx + i < W);
-#pragma unroll 4
-                for (int j = j0; j < j1; j++) {
-                    rp0 += T::RWP;
-                    const int a = rp0[0], bb = rp0[1], c = rp0[2];
-                    const int d2 = c - a, s2 = 3 * (a + c) + 10 * bb;
-                    int ix = 3 * (d0 + d2) + 10 * d1, iy = s2 - s0;
-                    if (!(col_ok && (inside || (ipy + j >= 0 && ipy + j < H)))) { ix = 0; iy = 0; }
-                    der[j * T::DWP + i] = make_short2((short)ix, (short)iy);
-                    d0 = d1; d1 = d2; s0 = s1; s1 = s2;
+        // PACKED (31x31): I*32 two per register, (Ix | Iy << 16) one per pixel; otherwise one register per value
+        constexpr bool PACKED = T::RPL * RUN > 16;
+        int tI[T::RPL][PACKED ? (RUN + 1) / 2 : RUN];
+        int tX[T::RPL][RUN];
+        int tY[T::RPL][PACKED ? 1 : RUN];
+        int a11 = 0, a12 = 0, a22 = 0;
+        auto put = [&](int k, int t, int iv, int ixv, int iyv) {
+            if (!run_ok[k]) { iv = 0; ixv = 0; iyv = 0; }
+            if (PACKED) {
+                if (t & 1) tI[k][t / 2] |= iv << 16; else tI[k][t / 2] = iv;
+                tX[k][t] = (ixv & 0xffff) | (iyv << 16);
+            } else { tI[k][t] = iv; tX[k][t] = ixv; tY[k][t] = iyv; }
+            a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv;
+        };
+        const bool inside = ipx >= 0 && ipy >= 0 && ipx + WW < W && ipy + WH < H;      // every derivative sample is in the level
+        if (inside) {
+            // 2a. Bilinear interpolation and the Scharr operator are both linear and cv2 rounds only once, after the
+            //     interpolation: Ix~ = (Scharr_x(U) + 2^13) >> 14 with U = sum_k w_k I(. + k) the un-rounded Q14 sums, and
+            //     I~ = (U + 2^8) >> 9.  U on the (WW+2)x(WH+2) grid: 2 DP2A per value (4 values per lane step).
+            int *U = reinterpret_cast<int *>(der);
+            const int wT = (w00 & 0xffff) | (w01 << 16), wB = (w10 & 0xffff) | (w11 << 16);
+            for (int sg = lane; sg < T::UH * T::USEG; sg += 32) {
+                const int row = sg / T::USEG, sx = (sg - row * T::USEG) * 4;
+                int u[4];
+                bilinear_run<4, false>(raw + row * T::RWP, raw + (row + 1) * T::RWP, ro + sx, wT, wB, u);
+                *reinterpret_cast<int4 *>(U + row * T::UP + sx) = make_int4(u[0], u[1], u[2], u[3]);
+            }
+            __syncwarp();
+            // 3a. template from U: window pixel (x, y) is U(x+1, y+1); its 3x3 Scharr support is U(x..x+2, y..y+2)
+            constexpr int CH = RUN <= 8 ? RUN : 8;
+#pragma unroll
+            for (int k = 0; k < T::RPL; k++) {
+                const int *u0 = U + run_y[k] * T::UP + run_x[k], *u1 = u0 + T::UP, *u2 = u1 + T::UP;
+#pragma unroll
+                for (int c0 = 0; c0 < RUN; c0 += CH) {
+                    constexpr int dummy = 0; (void)dummy;
+                    int p0[CH + 2], p1[CH + 2], p2[CH + 2];
+#pragma unroll
+                    for (int i = 0; i < CH + 2; i++)
+                        if (c0 + i < RUN + 2) { p0[i] = u0[c0 + i]; p1[i] = u1[c0 + i]; p2[i] = u2[c0 + i]; }
+#pragma unroll
+                    for (int i = 0; i < CH; i++) {
+                        if (c0 + i < RUN) {
+                            const int d0 = p0[i + 2] - p0[i], d1 = p1[i + 2] - p1[i], d2 = p2[i + 2] - p2[i];
+                            const int s0 = 3 * (p0[i] + p0[i + 2]) + 10 * p0[i + 1], s2 = 3 * (p2[i] + p2[i + 2]) + 10 * p2[i + 1];
+                            const int ixv = (3 * (d0 + d2) + 10 * d1 + (1 << 13)) >> 14;
+                            const int iyv = (s2 - s0 + (1 << 13)) >> 14;
+                            put(k, c0 + i, (p1[i + 1] + (1 << 8)) >> 9, ixv, iyv);
+                        }
+                    }
                 }
             }
-        }
-        __syncwarp();
-        // 3. template patch (registers) + structure tensor
-        unsigned pI[T::RPL][(RUN + 1) / 2];      // I*32 packed two per register
-        unsigned pD[T::RPL][RUN];                // (Ix & 0xffff) | Iy << 16
-        int a11 = 0, a12 = 0, a22 = 0;
+        } else {
+            // 2b/3b. window touches the border of the level (cold): derivative samples outside the level are ZERO (cv2's
+            //        zero-bordered derivative image) while image samples are mirrored, so the linearity shortcut does not
+            //        hold; a rolled, non-inlined routine leaves the template in shared memory.
+            short *bI = reinterpret_cast<short *>(brd);
+            short2 *bD = reinterpret_cast<short2 *>(brd + T::BRD_I_BYTES);
+            template_border<T>(raw, ro, der, bI, bD, ipx, ipy, W, H, w00, w01, w10, w11, lane);
 #pragma unroll
-        for (int k = 0; k < T::RPL; k++) {
-            const unsigned char *r0 = raw + (run_y[k] + 1) * T::RWP + ro + run_x[k] + 1, *r1 = r0 + T::RWP;
-            const short2 *d0 = der + run_y[k] * T::DWP + run_x[k], *d1 = d0 + T::DWP;
-            int i00 = r0[0], i10 = r1[0];
-            short2 e00 = d0[0], e10 = d1[0];
+            for (int k = 0; k < T::RPL; k++)
 #pragma unroll
-            for (int t = 0; t < RUN; t++) {
-                int i01 = r0[t + 1], i11 = r1[t + 1];
-                short2 e01 = d0[t + 1], e11 = d1[t + 1];
-                int iv = descale(i00 * w00 + i01 * w01 + i10 * w10 + i11 * w11, 9);
-                int ixv = descale(e00.x * w00 + e01.x * w01 + e10.x * w10 + e11.x * w11, 14);
-                int iyv = descale(e00.y * w00 + e01.y * w01 + e10.y * w10 + e11.y * w11, 14);
-                if (!run_ok[k]) { iv = 0; ixv = 0; iyv = 0; }
-                if (t & 1) pI[k][t / 2] |= (unsigned)iv << 16; else pI[k][t / 2] = (unsigned)iv;
-                pD[k][t] = ((unsigned)ixv & 0xffffu) | ((unsigned)iyv << 16);
-                a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv;
-                i00 = i01; i10 = i11; e00 = e01; e10 = e11;
-            }
+                for (int t = 0; t < RUN; t++) {
+                    const int idx = run_y[k] * WW + run_x[k] + t;
+                    const short2 d = bD[idx];
+                    put(k, t, bI[idx], d.x, d.y);
+                }
         }
         const float A11 = __fmul_rn((float)warp_sum(a11), FLT_SCALE);
         const float A12 = __fmul_rn((float)warp_sum(a12), FLT_SCALE);
@@ -500,28 +653,32 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
         D = __fdiv_rn(1.f, D);
         nx = __fsub_rn(nx, hx); ny = __fsub_rn(ny, hy);
         float pdx = 0.f, pdy = 0.f;
+        cp_async_wait<0>();          // the `next` tile (and, long since, the next level's raw)
+        tile_pending = false;
+        __syncwarp();
 
-        // samples `next` at (ix,iy) through the smem tile; f(k, t, value) for every owned window pixel
+        // samples `next` at (ix,iy) through the smem tile; f(k, t, J - I) for every owned window pixel
         auto sweep = [&](int ix, int iy, auto f) {
             int ox = ix - tx0, oy = iy - ty0;
             if (ox < 0 || oy < 0 || ox + WW + 1 > T::TWC || oy + WH + 1 > T::TH) {
                 __syncwarp();
                 place_tile<T>(ix, iy, W, H, tx0, ty0);
                 load_j_tile<T>(J, jrp, W, H, jal4, tx0, ty0, tile, lane);
+                cp_async_commit();
+                cp_async_wait<0>();
                 __syncwarp();
                 ox = ix - tx0; oy = iy - ty0;
             }
+            const int wT = (w00 & 0xffff) | (w01 << 16), wB = (w10 & 0xffff) | (w11 << 16);
 #pragma unroll
             for (int k = 0; k < T::RPL; k++) {
-                const unsigned char *r0 = tile + (oy + run_y[k]) * T::TWC + ox + run_x[k], *r1 = r0 + T::TWC;
-                int j00 = r0[0], j10 = r1[0];
+                const unsigned char *r0 = tile + (oy + run_y[k]) * T::TWC;
+                int v[RUN];
+                bilinear_run<RUN>(r0, r0 + T::TWC, ox + run_x[k], wT, wB, v);
 #pragma unroll
                 for (int t = 0; t < RUN; t++) {
-                    int j01 = r0[t + 1], j11 = r1[t + 1];
-                    int v = descale(j00 * w00 + j01 * w01 + j10 * w10 + j11 * w11, 9);
-                    int iv = (t & 1) ? (int)(pI[k][t / 2] >> 16) : (int)(pI[k][t / 2] & 0xffffu);
-                    f(k, t, run_ok[k] ? v - iv : 0);
-                    j00 = j01; j10 = j11;
+                    const int iv = PACKED ? ((t & 1) ? (int)((unsigned)tI[k][t / 2] >> 16) : (tI[k][t / 2] & 0xffff)) : tI[k][t];
+                    f(k, t, run_ok[k] ? v[t] - iv : 0);
                 }
             }
         };
@@ -534,7 +691,10 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
             }
             weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             int b1 = 0, b2 = 0;
-            sweep(inx, iny, [&](int k, int t, int diff) { b1 += diff * (int)(short)(pD[k][t] & 0xffffu); b2 += diff * ((int)pD[k][t] >> 16); });
+            sweep(inx, iny, [&](int k, int t, int diff) {
+                if (PACKED) { b1 += diff * (int)(short)(tX[k][t] & 0xffff); b2 += diff * (tX[k][t] >> 16); }
+                else { b1 += diff * tX[k][t]; b2 += diff * tY[k][t]; }
+            });
             iters++;
             const float fb1 = __fmul_rn((float)warp_sum(b1), FLT_SCALE);
             const float fb2 = __fmul_rn((float)warp_sum(b2), FLT_SCALE);
@@ -556,7 +716,7 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
             if (out_of_level(ex, ey, iex, iey, WW, WH, W, H)) { st = false; continue; }
             weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
             int se = 0;
-            sweep(iex, iey, [&](int, int, int diff) { se += diff < 0 ? -diff : diff; });
+            sweep(iex, iey, [&](int, int, int diff) { se += abs(diff); });
             ev = __fdiv_rn((float)warp_sum(se), (float)(32 * WW * WH));
         }
     }
@@ -642,9 +802,9 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     }
     int rc = 1;
     if (p->win_w == 21 && p->win_h == 21)
-        rc = launch_lk_t<21, 21, 7, 6, 22, 52, 10>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<21, 21, 7, 6, 22, 52, 8>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 15 && p->win_h == 15)
-        rc = launch_lk_t<15, 15, 5, 6, 17, 36, 12>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<15, 15, 5, 6, 17, 36, 8>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 31 && p->win_h == 31)
         rc = launch_lk_t<31, 31, 31, 6, 33, 52, 6>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     if (rc < 0) return rc;

@@ -20,6 +20,17 @@ elif op == "gftt":
 elif op == "process_img":
     for _ in range(3):
         ops.process_img(frames, out=gray)
+elif op == "lk":
+    from lk_optical_flow_method_b200.pipeline import PairPipeline
+    LK = dict(winSize=(21, 21), maxLevel=2, criteria=(3, 10, 0.03))
+    pipe = PairPipeline(B - 1, H, W, 2000, LK, None, 0)
+    pipe.prime(frames[0])
+    pipe.stage_process(frames[1:]); pipe.stage_pyramid()
+    e = ops.min_eigen(gray[:B - 1], 7)
+    cor, cnt = ops.gftt_select(e, None, 2000, 0.01, 7, 2000)
+    pipe.set_points(cor, cnt)
+    for _ in range(3):
+        pipe.stage_track()
 elif op == "pyrdown":
     for _ in range(3):
         l1 = ops.pyr_down(gray)
