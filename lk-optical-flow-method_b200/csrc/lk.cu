@@ -258,7 +258,7 @@ k_lk_track(LKLevels lv, int n_levels, int w, int h, int max_count, double eps2, 
 // per-warp shared-memory tile (window + MARGIN on every side, loaded once per level with aligned
 // 32-bit loads and re-centred only if the iterate walks out of it).
 // ---------------------------------------------------------------------------------------------
-constexpr int LKT_WARPS = 2;     // small CTAs: a CTA retires when its slowest feature converges
+constexpr int LKT_WARPS = 1;     // one feature per CTA: registers and shared memory are released the moment it converges
 
 template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_>
 struct LKT {
@@ -802,11 +802,11 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     }
     int rc = 1;
     if (p->win_w == 21 && p->win_h == 21)
-        rc = launch_lk_t<21, 21, 7, 6, 22, 52, 8>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<21, 21, 7, 6, 22, 52, 16>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 15 && p->win_h == 15)
-        rc = launch_lk_t<15, 15, 5, 6, 17, 36, 8>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<15, 15, 5, 6, 17, 36, 16>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 31 && p->win_h == 31)
-        rc = launch_lk_t<31, 31, 31, 6, 33, 52, 6>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<31, 31, 31, 6, 33, 52, 12>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     if (rc < 0) return rc;
     if (rc == LKF_OK) { LKF_LAUNCH_CHECK(ctx); return LKF_OK; }
     if (area <= 2048) {      // int32 lane partials cannot overflow (<= 64 px/lane * 8160*4080)
