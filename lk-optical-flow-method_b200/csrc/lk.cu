@@ -749,6 +749,250 @@ int launch_lk_t(const LKLevels &lv, int n_levels, int max_count, double eps, con
     return LKF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small windows (3x3, 5x5, 7x7; config C4: dense per-pixel flow with a 5x5 window): ONE THREAD per feature.
+// A 25-pixel window cannot occupy a warp, and a dense grid of features makes neighbouring threads read
+// overlapping neighbourhoods, so every load is served by L1.  The template lives in registers (packed 16-bit),
+// all window sums are exact int32 (AREA <= 49), everything is unrolled at compile time.  Same arithmetic and
+// control flow as the warp kernels: results are bit-identical to them.
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+__device__ __noinline__ void load_row_bytes_edge(const uint8_t *__restrict__ row, int W, int gx, uint32_t *w)
+{   // cold: the row segment touches the border of the level (or the plane is not 4-byte aligned)
+#pragma unroll 1
+    for (int i = 0; i < (NB + 3) / 4; i++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (4 * i + c < NB) v |= (uint32_t)row[reflect101(gx + 4 * i + c, W)] << (8 * c);
+        w[i] = v;
+    }
+}
+
+// NB consecutive bytes of row gy starting at column gx (REFLECT_101 outside the level), packed from byte 0 of w[0]
+template <int NB>
+__device__ __forceinline__ void load_row_bytes(const uint8_t *__restrict__ P, long long rp, int W, int H, bool al4, int gx, int gy,
+                                               uint32_t (&w)[(NB + 3) / 4])
+{
+    constexpr int NW = (NB + 3) / 4;
+    const uint8_t *row = P + (long long)reflect101(gy, H) * rp;
+    const int ax = (gx >> 2) << 2;
+    if (al4 && ax >= 0 && ax + 4 * (NW + 1) <= W) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(row + ax);
+        uint32_t t[NW + 1];
+#pragma unroll
+        for (int i = 0; i <= NW; i++) t[i] = __ldg(q + i);
+        const int sh = (gx & 3) * 8;
+#pragma unroll
+        for (int i = 0; i < NW; i++) w[i] = __funnelshift_r(t[i], t[i + 1], sh);
+    } else {
+        uint32_t tmp[NW];
+        load_row_bytes_edge<NB>(row, W, gx, tmp);
+#pragma unroll
+        for (int i = 0; i < NW; i++) w[i] = tmp[i];
+    }
+}
+template <int NW>
+__device__ __forceinline__ int byte_of(const uint32_t (&w)[NW], int c) { return (int)((w[c >> 2] >> (8 * (c & 3))) & 255u); }
+
+// bilinear Q14 sums of N pixels from two packed byte rows: v[t] = top(t) w00 + top(t+1) w01 + bot(t) w10 + bot(t+1) w11
+template <int N, int NW>
+__device__ __forceinline__ void bilinear_packed(const uint32_t (&top)[NW], const uint32_t (&bot)[NW], int first, int wT, int wB,
+                                                int (&v)[N])
+{
+#pragma unroll
+    for (int t = 0; t < N; t++) {
+        const int c = first + t, i = c >> 2, j = c & 3;
+        uint32_t wa, wc;
+        if (j & 1) {
+            wa = i + 1 < NW ? __funnelshift_r(top[i], top[i + 1], 8) : top[i] >> 8;
+            wc = i + 1 < NW ? __funnelshift_r(bot[i], bot[i + 1], 8) : bot[i] >> 8;
+        } else { wa = top[i]; wc = bot[i]; }
+        int acc = (j & 2) ? dp2a_hi(wT, wa, 0) : dp2a_lo(wT, wa, 0);
+        v[t] = (j & 2) ? dp2a_hi(wB, wc, acc) : dp2a_lo(wB, wc, acc);
+    }
+}
+
+template <int WW, int WH>
+__global__ void __launch_bounds__(128)
+k_lk_track_small(LKLevels lv, int n_levels, int max_count, double eps2, int flags, double min_eig_thr,
+                 const float *__restrict__ prev_pts, const int *__restrict__ counts, int max_pts,
+                 float *__restrict__ next_pts, uint8_t *__restrict__ status, float *__restrict__ err,
+                 int *__restrict__ iters_out, unsigned al4_mask, unsigned ial4_mask)
+{
+    constexpr int AREA = WW * WH, RW = WW + 3, NWR = (RW + 3) / 4, NWJ = (WW + 1 + 3) / 4;
+    static_assert(AREA <= 49, "exact int32 window sums");
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    const int n = counts ? counts[b] : max_pts;
+    if (pt >= n || pt >= max_pts) return;
+    const long long pidx = (long long)b * max_pts + pt;
+    const float ppx = prev_pts[2 * pidx], ppy = prev_pts[2 * pidx + 1];
+    const float hx = (WW - 1) * 0.5f, hy = (WH - 1) * 0.5f;
+    float npx = 0.f, npy = 0.f;
+    if (flags & LKF_OPTFLOW_USE_INITIAL_FLOW) { npx = next_pts[2 * pidx]; npy = next_pts[2 * pidx + 1]; }
+    bool st = true;
+    float ev = 0.f;
+    int iters = 0;
+    const float FLT_SCALE = 1.f / (1 << 20);
+
+    for (int l = n_levels - 1; l >= 0; --l) {
+        const int W = lv.W[l], H = lv.H[l];
+        const uint8_t *I = lv.prev[l] + (long long)b * lv.pip[l];
+        const uint8_t *J = lv.next[l] + (long long)b * lv.nip[l];
+        const long long irp = lv.prp[l], jrp = lv.nrp[l];
+        const bool jal4 = (al4_mask >> l) & 1u, ial4 = (ial4_mask >> l) & 1u;
+        const float sc = 1.f / (float)(1 << l);
+        float px = __fmul_rn(ppx, sc), py = __fmul_rn(ppy, sc);
+        float nx, ny;
+        if (l == n_levels - 1) {
+            if (flags & LKF_OPTFLOW_USE_INITIAL_FLOW) { nx = __fmul_rn(npx, sc); ny = __fmul_rn(npy, sc); }
+            else { nx = px; ny = py; }
+        } else { nx = __fmul_rn(npx, 2.f); ny = __fmul_rn(npy, 2.f); }
+        npx = nx; npy = ny;
+        px = __fsub_rn(px, hx); py = __fsub_rn(py, hy);
+        const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+        if (out_of_level(px, py, ipx, ipy, WW, WH, W, H)) {
+            if (l == 0) { st = false; ev = 0.f; }
+            continue;
+        }
+        int w00, w01, w10, w11;
+        weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+        int wT = (w00 & 0xffff) | (w01 << 16), wB = (w10 & 0xffff) | (w11 << 16);
+
+        // template: raw rows r = 0..WH+2 (image rows ipy-1+r, columns ipx-1 ..) stream through registers; the horizontal
+        // Scharr terms d (difference) and s ([3 10 3] smoothing) of the last three rows give derivative row j = r-2
+        // (zero outside the level), derivative rows y, y+1 and raw rows y+1, y+2 give template row y.
+        unsigned tI[(AREA + 1) / 2], tD[AREA];
+        int a11 = 0, a12 = 0, a22 = 0;
+        {
+            uint32_t raw[3][NWR];
+            int d[3][WW + 1], s[3][WW + 1];
+            int dIx[2][WW + 1], dIy[2][WW + 1];
+#pragma unroll
+            for (int r = 0; r < WH + 3; r++) {
+                load_row_bytes<RW>(I, irp, W, H, ial4, ipx - 1, ipy - 1 + r, raw[r % 3]);
+#pragma unroll
+                for (int i = 0; i <= WW; i++) {
+                    const int a = byte_of<NWR>(raw[r % 3], i), m = byte_of<NWR>(raw[r % 3], i + 1), c = byte_of<NWR>(raw[r % 3], i + 2);
+                    d[r % 3][i] = c - a;
+                    s[r % 3][i] = 3 * (a + c) + 10 * m;
+                }
+                if (r >= 2) {
+                    const int j = r - 2;
+                    const bool row_ok = ipy + j >= 0 && ipy + j < H;
+#pragma unroll
+                    for (int i = 0; i <= WW; i++) {
+                        const bool ok = row_ok && ipx + i >= 0 && ipx + i < W;
+                        dIx[j & 1][i] = ok ? 3 * (d[j % 3][i] + d[(j + 2) % 3][i]) + 10 * d[(j + 1) % 3][i] : 0;
+                        dIy[j & 1][i] = ok ? s[(j + 2) % 3][i] - s[j % 3][i] : 0;
+                    }
+                    if (j >= 1) {
+                        const int y = j - 1;
+                        int iv[WW];
+                        bilinear_packed<WW, NWR>(raw[(y + 1) % 3], raw[(y + 2) % 3], 1, wT, wB, iv);
+#pragma unroll
+                        for (int x = 0; x < WW; x++) {
+                            const int ivv = descale(iv[x], 9);
+                            const int ixv = descale(dIx[y & 1][x] * w00 + dIx[y & 1][x + 1] * w01 + dIx[(y + 1) & 1][x] * w10 +
+                                                    dIx[(y + 1) & 1][x + 1] * w11, 14);
+                            const int iyv = descale(dIy[y & 1][x] * w00 + dIy[y & 1][x + 1] * w01 + dIy[(y + 1) & 1][x] * w10 +
+                                                    dIy[(y + 1) & 1][x + 1] * w11, 14);
+                            const int idx = y * WW + x;
+                            if (idx & 1) tI[idx / 2] |= (unsigned)ivv << 16; else tI[idx / 2] = (unsigned)ivv;
+                            tD[idx] = ((unsigned)ixv & 0xffffu) | ((unsigned)iyv << 16);
+                            a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv;
+                        }
+                    }
+                }
+            }
+        }
+        const float A11 = __fmul_rn((float)a11, FLT_SCALE), A12 = __fmul_rn((float)a12, FLT_SCALE), A22 = __fmul_rn((float)a22, FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dd = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * WW * WH));
+        if (flags & LKF_OPTFLOW_LK_GET_MIN_EIGENVALS) ev = minEig;
+        if ((double)minEig < min_eig_thr || D < 1.1920929e-07f) {
+            if (l == 0) st = false;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        nx = __fsub_rn(nx, hx); ny = __fsub_rn(ny, hy);
+        float pdx = 0.f, pdy = 0.f;
+
+        // J - I~ over the window at integer origin (ix, iy) with the current weights; f(idx, diff)
+        auto sweep = [&](int ix, int iy, auto f) {
+            uint32_t top[NWJ], bot[NWJ];
+            load_row_bytes<WW + 1>(J, jrp, W, H, jal4, ix, iy, top);
+#pragma unroll
+            for (int y = 0; y < WH; y++) {
+                load_row_bytes<WW + 1>(J, jrp, W, H, jal4, ix, iy + y + 1, bot);
+                int v[WW];
+                bilinear_packed<WW, NWJ>(top, bot, 0, wT, wB, v);
+#pragma unroll
+                for (int x = 0; x < WW; x++) {
+                    const int idx = y * WW + x;
+                    const int iv = (idx & 1) ? (int)(tI[idx / 2] >> 16) : (int)(tI[idx / 2] & 0xffffu);
+                    f(idx, descale(v[x], 9) - iv);
+                }
+#pragma unroll
+                for (int i = 0; i < NWJ; i++) top[i] = bot[i];
+            }
+        };
+
+        for (int j = 0; j < max_count; j++) {
+            const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+            if (out_of_level(nx, ny, inx, iny, WW, WH, W, H)) {
+                if (l == 0) st = false;
+                break;
+            }
+            weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+            wT = (w00 & 0xffff) | (w01 << 16); wB = (w10 & 0xffff) | (w11 << 16);
+            int b1 = 0, b2 = 0;
+            sweep(inx, iny, [&](int idx, int diff) { b1 += diff * (int)(short)(tD[idx] & 0xffffu); b2 += diff * ((int)tD[idx] >> 16); });
+            iters++;
+            const float fb1 = __fmul_rn((float)b1, FLT_SCALE), fb2 = __fmul_rn((float)b2, FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            npx = __fadd_rn(nx, hx); npy = __fadd_rn(ny, hy);
+            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2) break;
+            if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+                npx = __fsub_rn(npx, __fmul_rn(dx, 0.5f));
+                npy = __fsub_rn(npy, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (st && l == 0 && !(flags & LKF_OPTFLOW_LK_GET_MIN_EIGENVALS)) {
+            const float ex = __fsub_rn(npx, hx), ey = __fsub_rn(npy, hy);
+            const int iex = __float2int_rd(ex), iey = __float2int_rd(ey);
+            if (out_of_level(ex, ey, iex, iey, WW, WH, W, H)) { st = false; continue; }
+            weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
+            wT = (w00 & 0xffff) | (w01 << 16); wB = (w10 & 0xffff) | (w11 << 16);
+            int se = 0;
+            sweep(iex, iey, [&](int, int diff) { se += abs(diff); });
+            ev = __fdiv_rn((float)se, (float)(32 * WW * WH));
+        }
+    }
+    next_pts[2 * pidx] = npx;
+    next_pts[2 * pidx + 1] = npy;
+    status[pidx] = st ? 1 : 0;
+    err[pidx] = st ? ev : 0.f;
+    if (iters_out) iters_out[pidx] = iters;
+}
+
+template <int WW, int WH>
+int launch_lk_small(const LKLevels &lv, int n_levels, int max_count, double eps, const lkf_lk_params *p, const float *prev_pts,
+                    const int32_t *pt_counts, int max_pts, float *next_pts, uint8_t *status, float *err, int32_t *iters,
+                    unsigned al4_mask, unsigned ial4_mask, int B, cudaStream_t s)
+{
+    dim3 grid((max_pts + 127) / 128, B);
+    k_lk_track_small<WW, WH><<<grid, 128, 0, s>>>(lv, n_levels, max_count, eps, p->flags, p->min_eig_threshold, prev_pts, pt_counts,
+                                                  max_pts, next_pts, status, err, iters, al4_mask, ial4_mask);
+    return LKF_OK;
+}
+
 size_t lk_per_warp_bytes(int w, int h)
 {
     size_t area = (size_t)w * h;
@@ -807,6 +1051,12 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
         rc = launch_lk_t<15, 15, 5, 6, 17, 36, 16>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 31 && p->win_h == 31)
         rc = launch_lk_t<31, 31, 31, 6, 33, 52, 12>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+    else if (p->win_w == 5 && p->win_h == 5)
+        rc = launch_lk_small<5, 5>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+    else if (p->win_w == 3 && p->win_h == 3)
+        rc = launch_lk_small<3, 3>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+    else if (p->win_w == 7 && p->win_h == 7)
+        rc = launch_lk_small<7, 7>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     if (rc < 0) return rc;
     if (rc == LKF_OK) { LKF_LAUNCH_CHECK(ctx); return LKF_OK; }
     if (area <= 2048) {      // int32 lane partials cannot overflow (<= 64 px/lane * 8160*4080)

@@ -33,6 +33,7 @@ CASES = [
     (860, 483, dict(maxCorners=5, qualityLevel=0.3, minDistance=7, blockSize=7)),       # feature_params VP.py:92-95
     (860, 483, dict(maxCorners=500, qualityLevel=0.01, minDistance=7, blockSize=7)),
     (1920, 1080, dict(maxCorners=2000, qualityLevel=0.01, minDistance=7, blockSize=7)),  # C2 points
+    (3840, 2160, dict(maxCorners=10000, qualityLevel=0.001, minDistance=3, blockSize=3)),  # C3 points
     (641, 359, dict(maxCorners=1000, qualityLevel=0.001, minDistance=3, blockSize=3)),
     (641, 359, dict(maxCorners=0, qualityLevel=0.05, minDistance=0, blockSize=3)),      # unlimited, no min distance
     (320, 240, dict(maxCorners=300, qualityLevel=0.01, minDistance=2.5, blockSize=5)),  # cvRound(2.5) = 2

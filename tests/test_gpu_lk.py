@@ -36,6 +36,7 @@ CASES = [
     # W, H, n, q, d, bs, win, maxLevel, criteria
     (860, 483, 500, 0.01, 7, 7, (15, 15), 2, (3, 10, 0.03)),       # script lk_params (VP.py:98-100)
     (1920, 1080, 2000, 0.01, 7, 7, (21, 21), 2, (3, 10, 0.03)),    # C2
+    (3840, 2160, 10000, 0.001, 3, 3, (31, 31), 3, (3, 10, 0.03)),  # C3: 4K, 10k features, 4-level pyramid, 31x31
     (641, 359, 300, 0.05, 3.5, 3, (31, 31), 4, (3, 30, 0.01)),     # cv2 defaults, level clamp
     (320, 240, 200, 0.01, 3, 3, (5, 5), 2, (3, 10, 0.03)),         # C4 window
     (320, 240, 200, 0.01, 3, 3, (9, 13), 3, (1, 7, 0.0)),          # non-square, COUNT only
@@ -136,3 +137,43 @@ def test_pyrlk_batched_device_api(oracle):
         agree, dflow, _ = _compare((n1[i, :k], st[i, :k].reshape(-1, 1), er[i, :k].reshape(-1, 1)), ref[:3])
         assert agree >= STATUS_MIN and dflow <= FLOW_TOL
         assert np.abs(it[i, :k] - ref[3]).mean() < 0.05          # same iteration counts (roofline op count)
+
+
+def _grid(W, H):
+    ys, xs = np.mgrid[0:H, 0:W]
+    return np.stack([xs.ravel(), ys.ravel()], 1).astype(np.float32).reshape(-1, 1, 2)
+
+
+@pytest.mark.parametrize("win,crit", [((5, 5), (3, 10, 0.03)), ((5, 5), (1, 1, 0.0)), ((3, 3), (3, 10, 0.03)), ((7, 7), (3, 10, 0.03))])
+def test_dense_flow_small_frame_matches_oracle(oracle, win, crit):
+    """C4 (dense per-pixel LK, small window, 3-level pyramid) on a frame the oracle finishes in seconds: every pixel of
+    the frame is a feature -- image borders, flat regions and out-of-range iterates included."""
+    import lk_optical_flow_method_b200.cv as cv
+    W, H = 200, 120
+    prev, nxt = processed_pair(W, H)
+    pts = _grid(W, H)
+    got = cv.calcOpticalFlowPyrLK(prev, nxt, pts, None, winSize=win, maxLevel=2, criteria=crit)
+    ref = oracle.pyrlk(prev, nxt, pts, win, 2, crit)
+    agree, dflow, derr = _compare(got, ref)
+    assert agree >= STATUS_MIN and dflow <= FLOW_TOL and derr <= 1e-2, (agree, dflow, derr)
+    assert (ref[1] == 0).any() and (ref[1] == 1).any()
+
+
+def test_dense_flow_1080p_full_grid(oracle):
+    """C4 at full size: 1920x1080 = 2 073 600 features, 5x5 window, 3 levels.  Features are independent, so (i) a strided
+    subset tracked alone must reproduce the dense run bit for bit, and (ii) that subset is checked against the oracle."""
+    import lk_optical_flow_method_b200.cv as cv
+    W, H = 1920, 1080
+    prev, nxt = processed_pair(W, H)
+    lk = dict(winSize=(5, 5), maxLevel=2, criteria=(3, 10, 0.03))
+    pts = _grid(W, H)
+    dense = cv.calcOpticalFlowPyrLK(prev, nxt, pts, None, **lk)
+    assert dense[0].shape == pts.shape and dense[1].shape == (W * H, 1)
+    sel = np.arange(0, W * H, 61)
+    sub = cv.calcOpticalFlowPyrLK(prev, nxt, np.ascontiguousarray(pts[sel]), None, **lk)
+    for a, b in zip(dense, sub):
+        assert np.array_equal(a[sel], b)
+    ref = oracle.pyrlk(prev, nxt, np.ascontiguousarray(pts[sel]), (5, 5), 2, (3, 10, 0.03))
+    agree, dflow, derr = _compare(sub, ref)
+    assert agree >= STATUS_MIN and dflow <= FLOW_TOL and derr <= 1e-2, (agree, dflow, derr)
+    assert 0.2 < dense[1].mean() < 1.0                   # a plausible share of pixels is trackable with a 5x5 window

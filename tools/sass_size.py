@@ -24,7 +24,7 @@ def main(obj, sub=None):
         if m:
             cur = (m.group(1), int(m.group(2)))
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln) and fn:
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln) and fn:
             per[fn][cur] += 1
     for f, c in sorted(per.items(), key=lambda kv: -sum(kv[1].values())):
         print(f"{sum(c.values()):6d}  {f[:110]}")
