@@ -39,6 +39,9 @@ WORKLOAD = ("C2: 1920x1080 sparse PyrLK, 2000 pts/pair, 3-level pyramid (maxLeve
             "criteria (EPS|COUNT,10,0.03); per pair process_img(BGR)+pyramid+LK; GFTT(2000,q=0.01,d=7,bs=7) "
             "refresh on every 10th pair")
 METRIC = "frame-pairs/s, 1080p PyrLK 2k pts"
+# dram__bytes_read.sum + dram__bytes_write.sum per frame pair, from the committed ncu --set full captures
+NCU_SOURCE = "profiles/r01_captureB_kernels.md (ncu --set full, per launch of 32 pairs, divided by 32)"
+NCU_DRAM_BYTES_PER_PAIR = {"lk_track": (87.9e6 + 4.2e6) / 32, "process_img": (199.1e6 + 66.4e6) / 32}
 
 
 def env_int(name, default):
@@ -324,25 +327,33 @@ def run_b200(args):
     d2h = sum(o.numel() * o.element_size() for o in outs[-1])
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- per-stage device times (eager, CUDA events around each stage) --------------------------
+    # ---- per-stage device times: each stage captured in its own CUDA graph and replayed back to back (no launch
+    #      gaps inside the timed region), CUDA events on the launch stream --------------------------------------
     stage_names = ["process_img", "pyramid", "gftt_refresh", "lk_track", "carry"]
     stage_fn = [lambda: pipe.stage_process(new_frames), pipe.stage_pyramid, pipe.stage_refresh,
-                lambda: pipe.stage_track(want_iters=True), pipe.stage_carry]
-    acc = np.zeros(len(stage_fn))
-    reps = max(3, min(K, 10))
-    for r in range(reps + 1):
-        pipe.set_points(pts)
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(stage_fn) + 1)]
-        evs[0].record()
-        for j, fn in enumerate(stage_fn):
-            fn()
-            evs[j + 1].record()
-        torch.cuda.synchronize()
-        if r:
-            acc += [evs[j].elapsed_time(evs[j + 1]) for j in range(len(stage_fn))]
-    st_ms = acc / reps
+                lambda: pipe.stage_track(want_iters=False), pipe.stage_carry]
+    pipe.set_points(pts)
+    pipe.step(new_frames)                      # state every stage graph replays on: points after one refresh
+    pipe.stage_track(want_iters=True)          # iteration counts for the op model (same points as the timed replays)
+    torch.cuda.synchronize()
     iters_total = int(pipe.iters.sum().item())
     n_tracked = int(pipe.counts.clamp(min=0).sum().item())
+    reps = max(5, min(K, 20))
+    st_ms = np.zeros(len(stage_fn))
+    for j, fn in enumerate(stage_fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        for _ in range(2):
+            g.replay()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b_.record()
+        torch.cuda.synchronize()
+        st_ms[j] = a.elapsed_time(b_) / reps
+        del g
 
     # ---- FP32 pipe peak probe ------------------------------------------------------------------
     import ctypes
@@ -383,17 +394,19 @@ def run_b200(args):
                                "achieved_TFLOPs": lk_tflops, "frac_of_fp32_peak": lk_tflops / fp32_peak})
     dom = stage_names[int(np.argmax(st_ms))]
     if dom == "lk_track":
-        roof = {"kernel": "k_lk_track", "bound": "fp32", "achieved": lk_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": lk_tflops / fp32_peak, "traffic": None,
+        roof = {"kernel": "k_lk_track_t<21,21>", "bound": "fp32", "achieved": lk_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": lk_tflops / fp32_peak,
+                "traffic": NCU_DRAM_BYTES_PER_PAIR["lk_track"] * B if B else None,
+                "traffic_source": NCU_SOURCE,
                 "peak_source": "measured in this run (FFMA probe kernel, non-tensor FP32 pipe)",
                 "note": "ALU-bound gather/iterate kernel; ops from the SURVEY 8d model with on-device iteration counts"}
     else:
         s_ = stages[dom]
         roof = {"kernel": dom, "bound": "hbm", "achieved": s_["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": s_["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src}
-    roof_hbm = {"kernel": "k_blur3<SrcBGR> (process_img)", "bound": "hbm", "achieved": stages["process_img"]["achieved_GBps"],
-                "peak": hbm_peak, "unit": "GB/s", "frac": stages["process_img"]["frac_of_hbm_peak"], "traffic": None,
-                "peak_source": peak_src}
+    roof_hbm = {"kernel": "k_blur3_stream<RowBGR> (process_img)", "bound": "hbm", "achieved": stages["process_img"]["achieved_GBps"],
+                "peak": hbm_peak, "unit": "GB/s", "frac": stages["process_img"]["frac_of_hbm_peak"],
+                "traffic": NCU_DRAM_BYTES_PER_PAIR["process_img"] * B, "traffic_source": NCU_SOURCE, "peak_source": peak_src}
 
     line = None
     if rank == 0:

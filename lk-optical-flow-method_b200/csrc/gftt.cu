@@ -92,6 +92,22 @@ k_min_eigen(const uint8_t *__restrict__ src, long long rp, long long ip, int H, 
     }
 }
 
+__device__ __forceinline__ unsigned f2key(float f)
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // order-preserving; 0 is below every float
+}
+__device__ __forceinline__ float key2f(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+constexpr int MAXM = 8;      // masks per image handled in one pass
+
+struct MaskSet {
+    const uint8_t *p; long long rp, ip; int per_image;   // per_image: 1 -> plane index b*n_masks+m, 0 -> m
+};
+
 // ---------------------------------------------------------------------------------------------
 // a5, streaming form for odd block sizes 3/5/7 on 4-byte aligned rows with W % 4 == 0 (860, 1920, 3840 ...): same
 // arithmetic as k_min_eigen, but every value is computed once and nothing is staged through CTA-wide barriers.
@@ -130,7 +146,8 @@ __device__ __forceinline__ double shfl_down_d(double v)
 template <int BS, bool EDGE>
 __device__ __forceinline__ void
 mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp, long long ip, int H, int W, float *__restrict__ dst,
-         long long drp, long long dip, int tail_cols, float s, float s2, int rows_per_strip, int dst_al16, int wx0)
+         long long drp, long long dip, int tail_cols, float s, float s2, int rows_per_strip, int dst_al16, int wx0,
+         MaskSet ms, int n_masks, unsigned *__restrict__ maxkey)
 {
     constexpr int R = MES<BS>::R, RING = MES<BS>::RING;
     const int b = blockIdx.z;
@@ -197,6 +214,10 @@ mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp,
         double2 *q = reinterpret_cast<double2 *>(ring + ((size_t)(row % RING) * 3 + ch) * 128);
         q[0] = make_double2(h[0], h[1]); q[32] = make_double2(h[2], h[3]);
     };
+    // fused a6 step 1: masked maximum of the map per (image, mask) as order-preserving keys (values are >= 0)
+    unsigned best[MAXM];
+#pragma unroll
+    for (int m = 0; m < MAXM; m++) best[m] = 0;
     auto emit_row = [&](int y, const double (&vxx)[4], const double (&vxy)[4], const double (&vyy)[4]) {
         if (!emit) return;
         float o[4];
@@ -207,8 +228,24 @@ mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp,
             o[j] = __fsub_rn(__fadd_rn(a, c2), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(bb, bb))));
         }
         float *q = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(dst) + (long long)b * dip + (long long)y * drp) + cx;
-        if (dst_al16) __stcs(reinterpret_cast<float4 *>(q), make_float4(o[0], o[1], o[2], o[3]));
+        if (dst_al16) *reinterpret_cast<float4 *>(q) = make_float4(o[0], o[1], o[2], o[3]);
         else { q[0] = o[0]; q[1] = o[1]; q[2] = o[2]; q[3] = o[3]; }
+        if (maxkey) {
+            unsigned k[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) k[j] = f2key(o[j]);
+            if (!ms.p) best[0] = max(best[0], max(max(k[0], k[1]), max(k[2], k[3])));
+            else {
+#pragma unroll
+                for (int m = 0; m < MAXM; m++) {
+                    if (m >= n_masks) break;
+                    const uint8_t *mp = ms.p + (long long)(ms.per_image ? b * n_masks + m : m) * ms.ip + (long long)y * ms.rp + cx;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (mp[j]) best[m] = max(best[m], k[j]);
+                }
+            }
+        }
     };
 
     // product rows ylo..yhi are computed in order; image rows ylo-1 .. yhi+1 (mirrored) feed them, prefetched MES_PF ahead
@@ -288,27 +325,35 @@ mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp,
         advance(ynext, hxx, hxy, hyy, oxx, oxy, oyy);
         ynext++;
     }
+    if (maxkey) {
+#pragma unroll
+        for (int m = 0; m < MAXM; m++) {
+            if (m >= n_masks) break;
+            const unsigned v = __reduce_max_sync(0xffffffffu, best[m]);
+            if (lane == 0 && v) atomicMax(&maxkey[b * n_masks + m], v);
+        }
+    }
 }
 
 template <int BS>
 __global__ void __launch_bounds__(MES_WARPS * 32)
 k_min_eigen_stream(const uint8_t *__restrict__ src, long long rp, long long ip, int H, int W, float *__restrict__ dst,
                    long long drp, long long dip, int tail_cols, float s, float s2, int rows_per_strip, int dst_al16,
-                   const int32_t *__restrict__ enable)
+                   const int32_t *__restrict__ enable, MaskSet ms, int n_masks, unsigned *__restrict__ maxkey)
 {
     extern __shared__ __align__(16) unsigned char mes_smem[];
     if (enable && !enable[blockIdx.z]) return;
     const int wx0 = (blockIdx.x * MES_WARPS + (threadIdx.x >> 5)) * MES_COLS;
     if (wx0 >= W) return;                                   // warp-uniform; the kernel has no CTA-wide barrier
     if (wx0 == 0 || wx0 + MES_COLS + 4 >= W)
-        mes_body<BS, true>(mes_smem, src, rp, ip, H, W, dst, drp, dip, tail_cols, s, s2, rows_per_strip, dst_al16, wx0);
+        mes_body<BS, true>(mes_smem, src, rp, ip, H, W, dst, drp, dip, tail_cols, s, s2, rows_per_strip, dst_al16, wx0, ms, n_masks, maxkey);
     else
-        mes_body<BS, false>(mes_smem, src, rp, ip, H, W, dst, drp, dip, tail_cols, s, s2, rows_per_strip, dst_al16, wx0);
+        mes_body<BS, false>(mes_smem, src, rp, ip, H, W, dst, drp, dip, tail_cols, s, s2, rows_per_strip, dst_al16, wx0, ms, n_masks, maxkey);
 }
 
 template <int BS>
 int launch_min_eigen_stream(lkf_ctx *ctx, const lkf_image *src, const lkf_image *eig, int tail, float s, float s2,
-                            const int32_t *enable, cudaStream_t st)
+                            const int32_t *enable, MaskSet ms, int n_masks, unsigned *maxkey, cudaStream_t st)
 {
     static bool attr = false;
     if (!attr) {
@@ -332,29 +377,13 @@ int launch_min_eigen_stream(lkf_ctx *ctx, const lkf_image *src, const lkf_image 
     dim3 grid(ctas_x, (H + rows - 1) / rows, B);
     k_min_eigen_stream<BS><<<grid, MES_WARPS * 32, MES<BS>::SMEM, st>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch, H, W,
                                                                         (float *)eig->data, eig->row_pitch, eig->image_pitch, tail, s, s2,
-                                                                        rows, aligned_to(eig, 16) ? 1 : 0, enable);
+                                                                        rows, aligned_to(eig, 16) ? 1 : 0, enable, ms, n_masks, maxkey);
     return LKF_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // a6 helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned f2key(float f)
-{
-    unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // order-preserving; 0 is below every float
-}
-__device__ __forceinline__ float key2f(unsigned k)
-{
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
-constexpr int MAXM = 8;      // masks per image handled in one pass
-
-struct MaskSet {
-    const uint8_t *p; long long rp, ip; int per_image;   // per_image: 1 -> plane index b*n_masks+m, 0 -> m
-};
-
 __global__ void __launch_bounds__(256)
 k_masked_max(const float *__restrict__ eig, long long erp, long long eip, int H, int W, MaskSet ms, int n_masks,
              unsigned *__restrict__ maxkey, const int32_t *__restrict__ enable)
@@ -397,21 +426,33 @@ k_nms_compact(const float *__restrict__ eig, long long erp, long long eip, int H
     const int y = 1 + blockIdx.y * 8 + (threadIdx.x >> 5);
     const unsigned char *e = reinterpret_cast<const unsigned char *>(eig) + (long long)b * eip;
     bool inside = x < W - 1 && y < H - 1;
+    // per-mask thresholds; the 3x3 neighbourhood is only fetched where the pixel survives the weakest of them
+    float thr_m[MAXM], thr_min = 3.4e38f;
+#pragma unroll
+    for (int m = 0; m < MAXM; m++) {
+        if (m >= n_masks) break;
+        const unsigned mk = maxkey[b * n_masks + m];
+        thr_m[m] = (float)((mk ? (double)key2f(mk) : 0.0) * quality);
+        thr_min = fminf(thr_min, thr_m[m]);
+    }
     float v = 0.f;
     bool is_max = false;
     if (inside) {
-        const float *r0 = reinterpret_cast<const float *>(e + (long long)(y - 1) * erp) + x;
         const float *r1 = reinterpret_cast<const float *>(e + (long long)y * erp) + x;
-        const float *r2 = reinterpret_cast<const float *>(e + (long long)(y + 1) * erp) + x;
         v = r1[0];
-        float m = fmaxf(fmaxf(fmaxf(r0[-1], r0[0]), fmaxf(r0[1], r1[-1])), fmaxf(fmaxf(r1[1], r2[-1]), fmaxf(r2[0], r2[1])));
-        is_max = v >= m;
+        if (v > thr_min && v != 0.f) {
+            const float *r0 = reinterpret_cast<const float *>(e + (long long)(y - 1) * erp) + x;
+            const float *r2 = reinterpret_cast<const float *>(e + (long long)(y + 1) * erp) + x;
+            float m = fmaxf(fmaxf(fmaxf(r0[-1], r0[0]), fmaxf(r0[1], r1[-1])), fmaxf(fmaxf(r1[1], r2[-1]), fmaxf(r2[0], r2[1])));
+            is_max = v >= m;
+        }
     }
-    for (int m = 0; m < n_masks; m++) {
+    if (!__any_sync(0xffffffffu, is_max)) return;
+#pragma unroll
+    for (int m = 0; m < MAXM; m++) {
+        if (m >= n_masks) break;
         const int list = b * n_masks + m;
-        unsigned mk = maxkey[list];
-        double max_val = mk ? (double)key2f(mk) : 0.0;
-        float thr = (float)(max_val * quality);
+        const float thr = thr_m[m];
         bool cand = inside && is_max && v > thr;          // v > thr >= ... ; thresholded neighbours are <= v
         if (cand && ms.p) cand = ms.p[(long long)(ms.per_image ? list : m) * ms.ip + (long long)y * ms.rp + x] != 0;
         // a thresholded map keeps v only if v > thr; "v != 0" then holds unless thr < 0 and v == 0
@@ -504,31 +545,38 @@ k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__
         __syncthreads();
         const float md2 = (float)(min_distance * min_distance);     // integer coordinates: d2 is exact
         const bool md2_exact = (double)md2 == min_distance * min_distance;
-        for (;;) {
-            int pending = 0;
-            for (int i = tid; i < n; i += SS_NT) {
-                if (state[i]) continue;
-                unsigned v = xy[2 * i];
-                int x = v & 0xffff, y = v >> 16;
-                int cx = x / cs, cy = y / cs;
-                int verdict = 1;
-                for (int yy = max(0, cy - 1); yy <= min(gh - 1, cy + 1) && verdict != 2; yy++)
-                    for (int xx = max(0, cx - 1); xx <= min(gw - 1, cx + 1) && verdict != 2; xx++)
-                        for (unsigned j = heads[yy * gw + xx]; j != SS_NIL; j = nxt[j]) {
-                            if ((int)j >= i) continue;
-                            unsigned u = xy[2 * j];
-                            float dx = (float)(x - (int)(u & 0xffff)), dy = (float)(y - (int)(u >> 16));
-                            float d2 = dx * dx + dy * dy;
-                            bool close = md2_exact ? (d2 < md2) : ((double)d2 < min_distance * min_distance);
-                            if (close) {
-                                unsigned sj = state[j];
-                                if (sj == 1) { verdict = 2; break; }
-                                if (sj == 0) verdict = 0;
+        // Rank-ordered windows of SS_NT candidates: every higher-ranked window is final, so only dependencies inside the
+        // window need fixed-point rounds (a few), and the scan stops as soon as maxCorners corners are accepted.
+        const int stop_at = (max_corners > 0 && max_corners <= max_out) ? max_corners : 0x7fffffff;
+        int accepted = 0;
+        for (int base = 0; base < n && accepted < stop_at; base += SS_NT) {
+            const int i = base + tid;
+            for (;;) {
+                int pending = 0;
+                if (i < n && !state[i]) {
+                    unsigned v = xy[2 * i];
+                    int x = v & 0xffff, y = v >> 16;
+                    int cx = x / cs, cy = y / cs;
+                    int verdict = 1;
+                    for (int yy = max(0, cy - 1); yy <= min(gh - 1, cy + 1) && verdict != 2; yy++)
+                        for (int xx = max(0, cx - 1); xx <= min(gw - 1, cx + 1) && verdict != 2; xx++)
+                            for (unsigned j = heads[yy * gw + xx]; j != SS_NIL; j = nxt[j]) {
+                                if ((int)j >= i) continue;
+                                unsigned u = xy[2 * j];
+                                float dx = (float)(x - (int)(u & 0xffff)), dy = (float)(y - (int)(u >> 16));
+                                float d2 = dx * dx + dy * dy;
+                                bool close = md2_exact ? (d2 < md2) : ((double)d2 < min_distance * min_distance);
+                                if (close) {
+                                    unsigned sj = state[j];
+                                    if (sj == 1) { verdict = 2; break; }
+                                    if (sj == 0) verdict = 0;
+                                }
                             }
-                        }
-                if (verdict) state[i] = (unsigned char)verdict; else pending = 1;
+                    if (verdict) state[i] = (unsigned char)verdict; else pending = 1;
+                }
+                if (!__syncthreads_or(pending)) break;
             }
-            if (!__syncthreads_or(pending)) break;
+            accepted += __syncthreads_count(i < n && state[i] == 1);
         }
     }
     __syncthreads();
@@ -568,9 +616,27 @@ k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__
 
 }  // namespace
 
-static int min_eigen_impl(lkf_ctx *ctx, const lkf_image *src, const lkf_image *eig, int block_size, int dy_tail_cols, const int32_t *enable,
-                          lkf_stream stream)
+static int make_mask_set(const lkf_image *mask, int n_masks, int B, int H, int W, MaskSet *out)
 {
+    MaskSet ms{nullptr, 0, 0, 0};
+    if (n_masks < 1 || n_masks > MAXM) return LKF_ERR_ARG;
+    if (mask) {
+        if (!img_ok(mask, 1, 1) || mask->height != H || mask->width != W) return LKF_ERR_ARG;
+        if (mask->batch == n_masks) ms.per_image = 0;
+        else if (mask->batch == B * n_masks) ms.per_image = 1;
+        else return LKF_ERR_ARG;
+        ms.p = (const uint8_t *)mask->data; ms.rp = mask->row_pitch; ms.ip = mask->image_pitch;
+    } else if (n_masks != 1) return LKF_ERR_ARG;
+    *out = ms;
+    return LKF_OK;
+}
+
+// maxkey != NULL: also reduce the masked maxima (a6 step 1) while the map is produced; *fused tells whether that happened
+static int min_eigen_impl(lkf_ctx *ctx, const lkf_image *src, const lkf_image *eig, int block_size, int dy_tail_cols, const int32_t *enable,
+                          lkf_stream stream, MaskSet ms = MaskSet{nullptr, 0, 0, 0}, int n_masks = 1, unsigned *maxkey = nullptr,
+                          bool *fused = nullptr)
+{
+    if (fused) *fused = false;
     if (!img_ok(src, 1, 1) || !img_ok(eig, 1, 4) || src->batch != eig->batch || src->height != eig->height ||
         src->width != eig->width || !aligned_to(eig, 4))
         return LKF_ERR_ARG;
@@ -582,10 +648,11 @@ static int min_eigen_impl(lkf_ctx *ctx, const lkf_image *src, const lkf_image *e
     const float s = (float)scale, s2 = (float)(2.0 * scale);
     if ((bs == 3 || bs == 5 || bs == 7) && W % 4 == 0 && W >= 8 && H >= 8 && aligned_to(src, 4)) {
         cudaStream_t st = (cudaStream_t)stream;
-        int rc = bs == 3 ? launch_min_eigen_stream<3>(ctx, src, eig, dy_tail_cols, s, s2, enable, st)
-               : bs == 5 ? launch_min_eigen_stream<5>(ctx, src, eig, dy_tail_cols, s, s2, enable, st)
-                         : launch_min_eigen_stream<7>(ctx, src, eig, dy_tail_cols, s, s2, enable, st);
+        int rc = bs == 3 ? launch_min_eigen_stream<3>(ctx, src, eig, dy_tail_cols, s, s2, enable, ms, n_masks, maxkey, st)
+               : bs == 5 ? launch_min_eigen_stream<5>(ctx, src, eig, dy_tail_cols, s, s2, enable, ms, n_masks, maxkey, st)
+                         : launch_min_eigen_stream<7>(ctx, src, eig, dy_tail_cols, s, s2, enable, ms, n_masks, maxkey, st);
         if (rc != LKF_OK) return rc;
+        if (fused && maxkey) *fused = true;
         LKF_LAUNCH_CHECK(nullptr);
         return LKF_OK;
     }
@@ -606,69 +673,92 @@ LKF_EXPORT int lkf_corner_min_eigen_f32(const lkf_image *src, const lkf_image *e
     return min_eigen_impl(nullptr, src, eig, block_size, dy_tail_cols, nullptr, stream);
 }
 
-static int gftt_select_impl(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *eig, const lkf_image *mask,
-                            int n_masks, const int32_t *enable, float *corners, int32_t *counts, int max_out, lkf_stream stream)
+struct GfttScratch {
+    unsigned long long *keys; unsigned *maxkey; int *ccount; void *gaux;
+    int cap, cs, gw, gh, lists;
+};
+
+// validates the selection arguments, sizes the scratch buffers and zeroes the per-list maxima / candidate counts
+static int gftt_prepare(lkf_ctx *ctx, const lkf_gftt_params *p, int B, int H, int W, int n_masks, float *corners, int32_t *counts,
+                        int max_out, lkf_stream stream, GfttScratch *g)
 {
-    if (!ctx || !p || !img_ok(eig, 1, 4) || !aligned_to(eig, 4) || !corners || !counts || max_out < 1) return LKF_ERR_ARG;
+    if (!ctx || !p || !corners || !counts || max_out < 1) return LKF_ERR_ARG;
     if (!(p->quality_level > 0) || p->min_distance < 0) return LKF_ERR_ARG;          // cv2 asserts
     if (n_masks < 1 || n_masks > MAXM) return LKF_ERR_ARG;
-    const int B = eig->batch, H = eig->height, W = eig->width;
-    MaskSet ms{nullptr, 0, 0, 0};
-    if (mask) {
-        if (!img_ok(mask, 1, 1) || mask->height != H || mask->width != W) return LKF_ERR_ARG;
-        if (mask->batch == n_masks) ms.per_image = 0;
-        else if (mask->batch == B * n_masks) ms.per_image = 1;
-        else return LKF_ERR_ARG;
-        ms.p = (const uint8_t *)mask->data; ms.rp = mask->row_pitch; ms.ip = mask->image_pitch;
-    } else if (n_masks != 1) return LKF_ERR_ARG;
-    if (H < 3 || W < 3) {        // no interior pixel: no corner
-        LKF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * B * n_masks, (cudaStream_t)stream));
-        return LKF_OK;
-    }
-    const int lists = B * n_masks;
+    if (W > 65535 || H > 65535) return LKF_ERR_UNSUPPORTED;
+    g->lists = B * n_masks;
     const long long P = (long long)H * W;
     long long cap_ll = P / 4 + 4096;
-    int cap = 32;
-    while (cap < cap_ll) cap <<= 1;
+    g->cap = 32;
+    while (g->cap < cap_ll) g->cap <<= 1;
     // neighbour grid: cell side >= minDistance (3x3 search suffices), grown until the heads fit in smem
-    int cs = 1, gw = 1, gh = 1;
+    g->cs = 1; g->gw = 1; g->gh = 1;
     if (p->min_distance >= 1) {
-        cs = (int)ceil(p->min_distance);
+        g->cs = (int)ceil(p->min_distance);
         for (;;) {
-            gw = (W + cs - 1) / cs; gh = (H + cs - 1) / cs;
-            if ((long long)gw * gh <= SS_MAX_CELLS) break;
-            cs++;
+            g->gw = (W + g->cs - 1) / g->cs; g->gh = (H + g->cs - 1) / g->cs;
+            if ((long long)g->gw * g->gh <= SS_MAX_CELLS) break;
+            g->cs++;
         }
     }
-    if (W > 65535 || H > 65535) return LKF_ERR_UNSUPPORTED;
-    const size_t ss_smem = (size_t)SS_SMEM_KEYS * 8 + (size_t)SS_MAX_CELLS * 4 + (size_t)SS_SMEM_KEYS * 4 + SS_SMEM_KEYS;
-    void *keys, *cnt, *gaux;
+    void *keys, *cnt;
     int rc;
-    if ((rc = lkf_scratch(ctx, 0, (size_t)lists * cap * 8, &keys)) != LKF_OK) return rc;
-    if ((rc = lkf_scratch(ctx, 1, (size_t)lists * 2 * sizeof(int), &cnt)) != LKF_OK) return rc;
-    if ((rc = lkf_scratch(ctx, 2, (size_t)lists * cap * 5, &gaux)) != LKF_OK) return rc;     // next (u32) + state (u8), large lists only
+    if ((rc = lkf_scratch(ctx, 0, (size_t)g->lists * g->cap * 8, &keys)) != LKF_OK) return rc;
+    if ((rc = lkf_scratch(ctx, 1, (size_t)g->lists * 2 * sizeof(int), &cnt)) != LKF_OK) return rc;
+    if ((rc = lkf_scratch(ctx, 2, (size_t)g->lists * g->cap * 5, &g->gaux)) != LKF_OK) return rc;     // next (u32) + state (u8), large lists only
+    g->keys = (unsigned long long *)keys;
+    g->maxkey = (unsigned *)cnt;
+    g->ccount = (int *)cnt + g->lists;
+    LKF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)g->lists * 2 * sizeof(int), (cudaStream_t)stream));
+    return LKF_OK;
+}
+
+static int gftt_passes(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *eig, MaskSet ms, int n_masks, const int32_t *enable,
+                       float *corners, int32_t *counts, int max_out, lkf_stream stream, const GfttScratch &g, bool max_done)
+{
+    const int B = eig->batch, H = eig->height, W = eig->width;
+    const long long P = (long long)H * W;
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned *maxkey = (unsigned *)cnt;
-    int *ccount = (int *)cnt + lists;
-    LKF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)lists * 2 * sizeof(int), s));
-    int chunks = (int)((P + 256 * 8 - 1) / (256 * 8));
-    if (chunks > 4 * ctx->sm_count) chunks = 4 * ctx->sm_count;
-    k_masked_max<<<dim3(chunks, B), 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, maxkey, enable);
-    LKF_LAUNCH_CHECK(ctx);
+    if (!max_done) {
+        int chunks = (int)((P + 256 * 8 - 1) / (256 * 8));
+        if (chunks > 4 * ctx->sm_count) chunks = 4 * ctx->sm_count;
+        k_masked_max<<<dim3(chunks, B), 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, g.maxkey, enable);
+        LKF_LAUNCH_CHECK(ctx);
+    }
     dim3 g2((W - 2 + 31) / 32, (H - 2 + 7) / 8, B);
-    k_nms_compact<<<g2, 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, maxkey,
-                                     p->quality_level, (unsigned long long *)keys, ccount, cap, enable);
+    k_nms_compact<<<g2, 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, g.maxkey,
+                                     p->quality_level, g.keys, g.ccount, g.cap, enable);
     LKF_LAUNCH_CHECK(ctx);
+    const size_t ss_smem = (size_t)SS_SMEM_KEYS * 8 + (size_t)SS_MAX_CELLS * 4 + (size_t)SS_SMEM_KEYS * 4 + SS_SMEM_KEYS;
     static bool ss_attr = false;
     if (!ss_attr) {
         LKF_CUDA(cudaFuncSetAttribute(k_sort_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_smem));
         ss_attr = true;
     }
-    k_sort_select<<<lists, SS_NT, ss_smem, s>>>((unsigned long long *)keys, ccount, cap, W, H, p->max_corners, p->min_distance, cs, gw,
-                                               gh, (unsigned *)gaux, (unsigned char *)gaux + (size_t)lists * cap * 4, corners, counts,
-                                               max_out, enable, n_masks);
+    k_sort_select<<<g.lists, SS_NT, ss_smem, s>>>(g.keys, g.ccount, g.cap, W, H, p->max_corners, p->min_distance, g.cs, g.gw,
+                                                 g.gh, (unsigned *)g.gaux, (unsigned char *)g.gaux + (size_t)g.lists * g.cap * 4, corners,
+                                                 counts, max_out, enable, n_masks);
     LKF_LAUNCH_CHECK(ctx);
     return LKF_OK;
+}
+
+static int gftt_select_impl(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *eig, const lkf_image *mask,
+                            int n_masks, const int32_t *enable, float *corners, int32_t *counts, int max_out, lkf_stream stream)
+{
+    if (!img_ok(eig, 1, 4) || !aligned_to(eig, 4)) return LKF_ERR_ARG;
+    const int B = eig->batch, H = eig->height, W = eig->width;
+    MaskSet ms;
+    int rc = make_mask_set(mask, n_masks, B, H, W, &ms);
+    if (rc != LKF_OK) return rc;
+    if (!ctx || !p || !corners || !counts || max_out < 1) return LKF_ERR_ARG;
+    if (!(p->quality_level > 0) || p->min_distance < 0) return LKF_ERR_ARG;          // cv2 asserts
+    if (H < 3 || W < 3) {        // no interior pixel: no corner
+        LKF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * B * n_masks, (cudaStream_t)stream));
+        return LKF_OK;
+    }
+    GfttScratch g;
+    if ((rc = gftt_prepare(ctx, p, B, H, W, n_masks, corners, counts, max_out, stream, &g)) != LKF_OK) return rc;
+    return gftt_passes(ctx, p, eig, ms, n_masks, enable, corners, counts, max_out, stream, g, false);
 }
 
 LKF_EXPORT int lkf_gftt_select(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *eig, const lkf_image *mask,
@@ -688,7 +778,19 @@ LKF_EXPORT int lkf_gftt_detect(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf
     int rc = lkf_scratch(ctx, 3, pitch * src->height * src->batch, &eigbuf);
     if (rc != LKF_OK) return rc;
     lkf_image eig = {eigbuf, src->batch, src->height, src->width, 1, (int64_t)pitch, (int64_t)(pitch * src->height)};
-    if ((rc = min_eigen_impl(ctx, src, &eig, p->block_size, p->dy_tail_cols, image_enable, stream)) != LKF_OK) return rc;
+    const int B = src->batch, H = src->height, W = src->width;
+    MaskSet ms;
+    if ((rc = make_mask_set(mask, n_masks, B, H, W, &ms)) != LKF_OK) return rc;
+    if (!corners || !counts || max_out < 1 || !(p->quality_level > 0) || p->min_distance < 0) return LKF_ERR_ARG;
+    if (H < 3 || W < 3) {
+        LKF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * B * n_masks, (cudaStream_t)stream));
+        return LKF_OK;
+    }
+    GfttScratch g;
+    if ((rc = gftt_prepare(ctx, p, B, H, W, n_masks, corners, counts, max_out, stream, &g)) != LKF_OK) return rc;
+    bool fused = false;
+    if ((rc = min_eigen_impl(ctx, src, &eig, p->block_size, p->dy_tail_cols, image_enable, stream, ms, n_masks, g.maxkey, &fused)) != LKF_OK)
+        return rc;
     lkf_count_launch(ctx);
-    return gftt_select_impl(ctx, p, &eig, mask, n_masks, image_enable, corners, counts, max_out, stream);
+    return gftt_passes(ctx, p, &eig, ms, n_masks, image_enable, corners, counts, max_out, stream, g, fused);
 }

@@ -43,7 +43,6 @@ class PairPipeline:
         self.iters = None
         self.R = len(range(0, self.B, self.refresh_every)) if self.refresh_every > 0 else 0
         if self.R:
-            self.eig = torch.zeros((self.R, H, W), dtype=torch.float32, device=self.dev)
             self.corners = torch.zeros((self.R, self.N, 2), dtype=torch.float32, device=self.dev)
             self.ccounts = torch.zeros((self.R,), dtype=torch.int32, device=self.dev)
         self.graph = None
@@ -72,9 +71,9 @@ class PairPipeline:
         if not self.R:
             return
         e = self.refresh_every
-        ops.min_eigen(self.levels[0][0:self.B:e], self.gftt["blockSize"], out=self.eig)
-        ops.gftt_select(self.eig, None, self.gftt["maxCorners"], self.gftt["qualityLevel"], self.gftt["minDistance"],
-                        self.N, out=(self.corners, self.ccounts))
+        # a5+a6 in one ABI call: the masked maximum is reduced while the eig map is produced (map in the workspace)
+        ops.gftt_detect(self.levels[0][0:self.B:e], None, self.gftt["maxCorners"], self.gftt["qualityLevel"],
+                        self.gftt["minDistance"], self.gftt["blockSize"], self.N, out=(self.corners, self.ccounts))
         self.pts[0:self.B:e].copy_(self.corners)
         self.counts[0:self.B:e].copy_(self.ccounts)
 
