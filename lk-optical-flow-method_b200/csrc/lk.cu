@@ -262,7 +262,7 @@ constexpr int LKT_WARPS = 1;     // one feature per CTA: registers and shared me
 
 template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_>
 struct LKT {
-    static constexpr int AREA = WW * WH, WW_ = WW, WH_ = WH;
+    static constexpr int AREA = WW * WH, WW_ = WW, WH_ = WH, RUN_ = RUN;
     static constexpr int RPR = WW / RUN;                 // runs per window row
     static constexpr int NRUNS = RPR * WH;
     static constexpr int RPL = (NRUNS + 31) / 32;        // runs per lane
@@ -280,8 +280,10 @@ struct LKT {
     static constexpr int DER_ONLY = (DWP * DH * 4 + 15) & ~15, U_BYTES = (UP * UH * 4 + 15) & ~15;
     static constexpr int DER_BYTES = DER_ONLY > U_BYTES ? DER_ONLY : U_BYTES, TILE_BYTES = (TWC * TH + 15) & ~15;
     static constexpr int RAW_BYTES = ((RWP * RH + 15) & ~15) + 16;     // + slack: word loaders read up to 2 words past a run
-    static constexpr int BRD_I_BYTES = (AREA * 2 + 15) & ~15, BRD_BYTES = BRD_I_BYTES + ((AREA * 4 + 15) & ~15);   // border template hand-over
-    static constexpr int PER_WARP = DER_BYTES + TILE_BYTES + 2 * RAW_BYTES + BRD_BYTES;      // raw is double-buffered
+    // template patch in shared memory, run-major: per run RUN x int16 (I*32) then RUN x (Ix, Iy) int16 pairs, 16-byte slots
+    static constexpr int TPL_I_BYTES = (RUN * 2 + 15) & ~15, TPL_D_BYTES = (RUN * 4 + 15) & ~15, TPL_RUN_BYTES = TPL_I_BYTES + TPL_D_BYTES;
+    static constexpr int TPL_BYTES = TPL_RUN_BYTES * 32 * RPL;
+    static constexpr int PER_WARP = DER_BYTES + TILE_BYTES + 2 * RAW_BYTES + TPL_BYTES;      // raw is double-buffered
     static_assert(WW % RUN == 0, "RUN must divide the window width");
     static_assert(AREA <= 2048, "int32 lane partials");
     static_assert(TWC % 4 == 0 && TWC >= WW + 1 + 2 * MARGIN + 3, "tile pitch");
@@ -445,7 +447,7 @@ __device__ __forceinline__ int load_raw(const uint8_t *__restrict__ I, long long
 // Template of a window that touches the border of the level: Scharr on the (WW+1)x(WH+1) sample grid with ZERO outside
 // the level, then the Q14 bilinear patch (I*32, Ix, Ix) for every window pixel -> shared memory (oI, oD).
 template <class T>
-__device__ __noinline__ void template_border(const unsigned char *raw, int ro, short2 *der, short *oI, short2 *oD, int ipx, int ipy,
+__device__ __noinline__ void template_border(const unsigned char *raw, int ro, short2 *der, unsigned char *tpl, int ipx, int ipy,
                                              int W, int H, int w00, int w01, int w10, int w11, int lane)
 {
 #pragma unroll 1
@@ -467,9 +469,12 @@ __device__ __noinline__ void template_border(const unsigned char *raw, int ro, s
         const unsigned char *r0 = raw + (y + 1) * T::RWP + ro + x + 1, *r1 = r0 + T::RWP;
         const short2 d00 = der[y * T::DWP + x], d01 = der[y * T::DWP + x + 1], d10 = der[(y + 1) * T::DWP + x],
                      d11 = der[(y + 1) * T::DWP + x + 1];
-        oI[idx] = (short)descale(r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11, 9);
-        oD[idx] = make_short2((short)descale(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14),
-                              (short)descale(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14));
+        const int run = y * T::RPR + x / T::RUN_, t = x % T::RUN_;
+        unsigned char *slot = tpl + run * T::TPL_RUN_BYTES;
+        reinterpret_cast<short *>(slot)[t] = (short)descale(r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11, 9);
+        reinterpret_cast<short2 *>(slot + T::TPL_I_BYTES)[t] =
+            make_short2((short)descale(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14),
+                        (short)descale(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14));
     }
     __syncwarp();
 }
@@ -492,7 +497,7 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
     short2 *der = reinterpret_cast<short2 *>(uni);          // Scharr on the sample grid (setup phase)
     unsigned char *tile = uni + T::DER_BYTES;                // `next` tile (prefetched at level entry)
     unsigned char *raw_buf = tile + T::TILE_BYTES;          // raw[l & 1]: template neighbourhood of level l (prefetched one level ahead)
-    unsigned char *brd = raw_buf + 2 * T::RAW_BYTES;
+    unsigned char *tpl = raw_buf + 2 * T::RAW_BYTES;        // template patch, run-major (this lane's runs: lane + 32 k)
 
     // this lane's runs: (row, first column) -- compile-time count, runtime validity
     int run_y[T::RPL], run_x[T::RPL];
@@ -570,20 +575,7 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
         const int ro = ial4 ? (ipx - 1) - (((ipx - 1) >> 2) << 2) : 0;
         cp_async_wait<2>();
         __syncwarp();
-        // PACKED (31x31): I*32 two per register, (Ix | Iy << 16) one per pixel; otherwise one register per value
-        constexpr bool PACKED = T::RPL * RUN > 16;
-        int tI[T::RPL][PACKED ? (RUN + 1) / 2 : RUN];
-        int tX[T::RPL][RUN];
-        int tY[T::RPL][PACKED ? 1 : RUN];
         int a11 = 0, a12 = 0, a22 = 0;
-        auto put = [&](int k, int t, int iv, int ixv, int iyv) {
-            if (!run_ok[k]) { iv = 0; ixv = 0; iyv = 0; }
-            if (PACKED) {
-                if (t & 1) tI[k][t / 2] |= iv << 16; else tI[k][t / 2] = iv;
-                tX[k][t] = (ixv & 0xffff) | (iyv << 16);
-            } else { tI[k][t] = iv; tX[k][t] = ixv; tY[k][t] = iyv; }
-            a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv;
-        };
         const bool inside = ipx >= 0 && ipy >= 0 && ipx + WW < W && ipy + WH < H;      // every derivative sample is in the level
         if (inside) {
             // 2a. Bilinear interpolation and the Scharr operator are both linear and cv2 rounds only once, after the
@@ -598,14 +590,21 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
                 *reinterpret_cast<int4 *>(U + row * T::UP + sx) = make_int4(u[0], u[1], u[2], u[3]);
             }
             __syncwarp();
-            // 3a. template from U: window pixel (x, y) is U(x+1, y+1); its 3x3 Scharr support is U(x..x+2, y..y+2)
+            // 3a. template from U: window pixel (x, y) is U(x+1, y+1); its 3x3 Scharr support is U(x..x+2, y..y+2).
+            //     Packed to int16 and stored run-major in shared memory; lanes whose run does not exist store zeros
+            //     (their products then vanish in every sum, no per-pixel predicate anywhere).
             constexpr int CH = RUN <= 8 ? RUN : 8;
 #pragma unroll
             for (int k = 0; k < T::RPL; k++) {
                 const int *u0 = U + run_y[k] * T::UP + run_x[k], *u1 = u0 + T::UP, *u2 = u1 + T::UP;
+                uint32_t wI[T::TPL_I_BYTES / 4], wD[T::TPL_D_BYTES / 4];
+#pragma unroll
+                for (int i = 0; i < T::TPL_I_BYTES / 4; i++) wI[i] = 0;
+#pragma unroll
+                for (int i = 0; i < T::TPL_D_BYTES / 4; i++) wD[i] = 0;
+                int s11 = 0, s12 = 0, s22 = 0;
 #pragma unroll
                 for (int c0 = 0; c0 < RUN; c0 += CH) {
-                    constexpr int dummy = 0; (void)dummy;
                     int p0[CH + 2], p1[CH + 2], p2[CH + 2];
 #pragma unroll
                     for (int i = 0; i < CH + 2; i++)
@@ -613,30 +612,44 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
 #pragma unroll
                     for (int i = 0; i < CH; i++) {
                         if (c0 + i < RUN) {
+                            const int t = c0 + i;
                             const int d0 = p0[i + 2] - p0[i], d1 = p1[i + 2] - p1[i], d2 = p2[i + 2] - p2[i];
                             const int s0 = 3 * (p0[i] + p0[i + 2]) + 10 * p0[i + 1], s2 = 3 * (p2[i] + p2[i + 2]) + 10 * p2[i + 1];
                             const int ixv = (3 * (d0 + d2) + 10 * d1 + (1 << 13)) >> 14;
                             const int iyv = (s2 - s0 + (1 << 13)) >> 14;
-                            put(k, c0 + i, (p1[i + 1] + (1 << 8)) >> 9, ixv, iyv);
+                            const int iv = (p1[i + 1] + (1 << 8)) >> 9;
+                            if (t & 1) wI[t / 2] |= (uint32_t)iv << 16; else wI[t / 2] = (uint32_t)iv;
+                            wD[t] = ((uint32_t)ixv & 0xffffu) | ((uint32_t)iyv << 16);
+                            s11 += ixv * ixv; s12 += ixv * iyv; s22 += iyv * iyv;
                         }
                     }
                 }
+                const uint32_t okm = run_ok[k] ? 0xffffffffu : 0u;
+                uint4 *slot = reinterpret_cast<uint4 *>(tpl + (lane + 32 * k) * T::TPL_RUN_BYTES);
+#pragma unroll
+                for (int i = 0; i < T::TPL_I_BYTES / 16; i++)
+                    slot[i] = make_uint4(wI[4 * i] & okm, wI[4 * i + 1] & okm, wI[4 * i + 2] & okm, wI[4 * i + 3] & okm);
+#pragma unroll
+                for (int i = 0; i < T::TPL_D_BYTES / 16; i++)
+                    slot[T::TPL_I_BYTES / 16 + i] = make_uint4(wD[4 * i] & okm, wD[4 * i + 1] & okm, wD[4 * i + 2] & okm, wD[4 * i + 3] & okm);
+                if (run_ok[k]) { a11 += s11; a12 += s12; a22 += s22; }
             }
         } else {
             // 2b/3b. window touches the border of the level (cold): derivative samples outside the level are ZERO (cv2's
             //        zero-bordered derivative image) while image samples are mirrored, so the linearity shortcut does not
-            //        hold; a rolled, non-inlined routine leaves the template in shared memory.
-            short *bI = reinterpret_cast<short *>(brd);
-            short2 *bD = reinterpret_cast<short2 *>(brd + T::BRD_I_BYTES);
-            template_border<T>(raw, ro, der, bI, bD, ipx, ipy, W, H, w00, w01, w10, w11, lane);
+            //        hold; a rolled, non-inlined routine writes the template (run-major) and the lanes re-read their runs.
+            for (int i = lane; i < T::TPL_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(tpl)[i] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            template_border<T>(raw, ro, der, tpl, ipx, ipy, W, H, w00, w01, w10, w11, lane);
 #pragma unroll
-            for (int k = 0; k < T::RPL; k++)
+            for (int k = 0; k < T::RPL; k++) {
+                const short2 *d = reinterpret_cast<const short2 *>(tpl + (lane + 32 * k) * T::TPL_RUN_BYTES + T::TPL_I_BYTES);
 #pragma unroll
                 for (int t = 0; t < RUN; t++) {
-                    const int idx = run_y[k] * WW + run_x[k] + t;
-                    const short2 d = bD[idx];
-                    put(k, t, bI[idx], d.x, d.y);
+                    const short2 e = d[t];
+                    a11 += e.x * e.x; a12 += e.x * e.y; a22 += e.y * e.y;
                 }
+            }
         }
         const float A11 = __fmul_rn((float)warp_sum(a11), FLT_SCALE);
         const float A12 = __fmul_rn((float)warp_sum(a12), FLT_SCALE);
@@ -675,10 +688,22 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
                 const unsigned char *r0 = tile + (oy + run_y[k]) * T::TWC;
                 int v[RUN];
                 bilinear_run<RUN>(r0, r0 + T::TWC, ox + run_x[k], wT, wB, v);
+                const uint4 *slot = reinterpret_cast<const uint4 *>(tpl + (lane + 32 * k) * T::TPL_RUN_BYTES);
+                uint32_t wI[T::TPL_I_BYTES / 4], wD[T::TPL_D_BYTES / 4];
+#pragma unroll
+                for (int i = 0; i < T::TPL_I_BYTES / 16; i++) {
+                    const uint4 q = slot[i];
+                    wI[4 * i] = q.x; wI[4 * i + 1] = q.y; wI[4 * i + 2] = q.z; wI[4 * i + 3] = q.w;
+                }
+#pragma unroll
+                for (int i = 0; i < T::TPL_D_BYTES / 16; i++) {
+                    const uint4 q = slot[T::TPL_I_BYTES / 16 + i];
+                    wD[4 * i] = q.x; wD[4 * i + 1] = q.y; wD[4 * i + 2] = q.z; wD[4 * i + 3] = q.w;
+                }
 #pragma unroll
                 for (int t = 0; t < RUN; t++) {
-                    const int iv = PACKED ? ((t & 1) ? (int)((unsigned)tI[k][t / 2] >> 16) : (tI[k][t / 2] & 0xffff)) : tI[k][t];
-                    f(k, t, run_ok[k] ? v[t] - iv : 0);
+                    const int iv = (t & 1) ? (int)(wI[t / 2] >> 16) : (int)(wI[t / 2] & 0xffffu);
+                    f(k, v[t] - iv, wD[t]);
                 }
             }
         };
@@ -691,10 +716,8 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
             }
             weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             int b1 = 0, b2 = 0;
-            sweep(inx, iny, [&](int k, int t, int diff) {
-                if (PACKED) { b1 += diff * (int)(short)(tX[k][t] & 0xffff); b2 += diff * (tX[k][t] >> 16); }
-                else { b1 += diff * tX[k][t]; b2 += diff * tY[k][t]; }
-            });
+            // (runs that do not exist hold a zero template: their terms vanish)
+            sweep(inx, iny, [&](int, int diff, uint32_t d) { b1 += diff * (int)(short)(d & 0xffffu); b2 += diff * ((int)d >> 16); });
             iters++;
             const float fb1 = __fmul_rn((float)warp_sum(b1), FLT_SCALE);
             const float fb2 = __fmul_rn((float)warp_sum(b2), FLT_SCALE);
@@ -716,7 +739,7 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
             if (out_of_level(ex, ey, iex, iey, WW, WH, W, H)) { st = false; continue; }
             weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
             int se = 0;
-            sweep(iex, iey, [&](int, int, int diff) { se += abs(diff); });
+            sweep(iex, iey, [&](int k, int diff, uint32_t) { se += run_ok[k] ? abs(diff) : 0; });
             ev = __fdiv_rn((float)warp_sum(se), (float)(32 * WW * WH));
         }
     }
@@ -1046,11 +1069,11 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     }
     int rc = 1;
     if (p->win_w == 21 && p->win_h == 21)
-        rc = launch_lk_t<21, 21, 7, 6, 22, 52, 16>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<21, 21, 7, 6, 22, 52, 24>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 15 && p->win_h == 15)
-        rc = launch_lk_t<15, 15, 5, 6, 17, 36, 16>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<15, 15, 5, 6, 17, 36, 24>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 31 && p->win_h == 31)
-        rc = launch_lk_t<31, 31, 31, 6, 33, 52, 12>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<31, 31, 31, 6, 33, 52, 16>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 5 && p->win_h == 5)
         rc = launch_lk_small<5, 5>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 3 && p->win_h == 3)
