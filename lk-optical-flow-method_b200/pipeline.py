@@ -9,8 +9,11 @@ corners replace that pair's points -- the REPlace refresh of VP.py:700-718 (TP_U
 Frame i's pyramid serves as `next` of pair i and `prev` of pair i+1, so each frame is processed once
 (the scripts' cv2 calls rebuild both pyramids on every call, VP.py:545).
 
-All launches go to the current CUDA stream without host synchronisation; `capture()` records the step
-into a CUDA graph.
+All launches are enqueued without host synchronisation; `capture()` records the step into a CUDA graph.
+Inside a step the corner refresh (a latency-bound chain: one sort/selection CTA per image) runs on a second,
+high-priority stream together with the LK launch of the refreshed pairs, concurrently with the LK launch of all
+other pairs on the main stream (fork after the pyramids, join before the carry).  The GFTT scratch of the workspace
+is only ever touched from that second stream.
 """
 import torch
 
@@ -45,6 +48,15 @@ class PairPipeline:
         if self.R:
             self.corners = torch.zeros((self.R, self.N, 2), dtype=torch.float32, device=self.dev)
             self.ccounts = torch.zeros((self.R,), dtype=torch.int32, device=self.dev)
+            # refreshed pairs are tracked by their own launch (second stream); the main launch skips them
+            self.main_mask = torch.ones((self.B,), dtype=torch.int32, device=self.dev)
+            self.main_mask[0:self.B:self.refresh_every] = 0
+            self.counts_main = torch.zeros_like(self.counts)
+            self.r_next = torch.zeros((self.R, self.N, 2), dtype=torch.float32, device=self.dev)
+            self.r_status = torch.zeros((self.R, self.N), dtype=torch.uint8, device=self.dev)
+            self.r_err = torch.zeros((self.R, self.N), dtype=torch.float32, device=self.dev)
+            self.aux = torch.cuda.Stream(device=self.dev, priority=-1)
+        self.overlap = True
         self.graph = None
 
     # -- state -----------------------------------------------------------------------------------
@@ -60,12 +72,15 @@ class PairPipeline:
             self.counts.copy_(counts)
 
     # -- stages (each is one kernel launch or a fixed short sequence) -----------------------------
-    def stage_process(self, bgr):
-        ops.process_img(bgr, out=self.levels[0][1:])
+    def stage_process(self, bgr, lo=0, hi=None):
+        """process_img of new frames lo..hi-1 (pyramid slots lo+1..hi)."""
+        hi = self.B if hi is None else hi
+        ops.process_img(bgr[lo:hi], out=self.levels[0][1 + lo:1 + hi])
 
-    def stage_pyramid(self):
+    def stage_pyramid(self, lo=0, hi=None):
+        hi = self.B if hi is None else hi
         for l in range(1, self.n_levels):
-            ops.pyr_down(self.levels[l - 1][1:], out=self.levels[l][1:])
+            ops.pyr_down(self.levels[l - 1][1 + lo:1 + hi], out=self.levels[l][1 + lo:1 + hi])
 
     def stage_refresh(self):
         if not self.R:
@@ -89,12 +104,62 @@ class PairPipeline:
         for lv in self.levels:
             lv[0].copy_(lv[self.B])
 
+    def stage_track_main(self, lo=0, hi=None):
+        """LK of pairs lo..hi-1 that are NOT refreshed in this step (point count 0 for the refreshed ones)."""
+        hi = self.B if hi is None else hi
+        torch.mul(self.counts[lo:hi], self.main_mask[lo:hi], out=self.counts_main[lo:hi])
+        prev = [lv[lo:hi] for lv in self.levels]
+        nxt = [lv[lo + 1:hi + 1] for lv in self.levels]
+        ops.pyrlk(prev, nxt, self.pts[lo:hi], self.params, counts=self.counts_main[lo:hi],
+                  out=(self.next_pts[lo:hi], self.status[lo:hi], self.err[lo:hi]))
+
+    def stage_refresh_detect(self):
+        """Corner refresh of every refresh_every-th pair (needs level 0 of the previous frames only)."""
+        e = self.refresh_every
+        ops.gftt_detect(self.levels[0][0:self.B:e], None, self.gftt["maxCorners"], self.gftt["qualityLevel"],
+                        self.gftt["minDistance"], self.gftt["blockSize"], self.N, out=(self.corners, self.ccounts))
+
+    def stage_track_refreshed(self):
+        """LK launch of exactly the refreshed pairs (strided views of the pyramid slots), results scattered into the
+        per-pair outputs."""
+        e = self.refresh_every
+        prev = [lv[0:self.B:e] for lv in self.levels]
+        nxt = [lv[1:self.B + 1:e] for lv in self.levels]
+        ops.pyrlk(prev, nxt, self.corners, self.params, counts=self.ccounts, out=(self.r_next, self.r_status, self.r_err))
+        self.pts[0:self.B:e].copy_(self.corners)
+        self.counts[0:self.B:e].copy_(self.ccounts)
+        self.next_pts[0:self.B:e].copy_(self.r_next)
+        self.status[0:self.B:e].copy_(self.r_status)
+        self.err[0:self.B:e].copy_(self.r_err)
+
     def step(self, bgr):
         """bgr: [B,H,W,3] uint8 CUDA tensor = the B new frames of this step."""
+        if not (self.R and self.overlap):
+            self.stage_process(bgr)
+            self.stage_pyramid()
+            self.stage_refresh()
+            self.stage_track()
+            self.stage_carry()
+            return
+        # Fork: the refresh chain only needs level 0, so it starts next to the pyramid build and its one-CTA-per-image
+        # sort/selection is already resident when the main LK launch fills the machine; the LK launch of the refreshed
+        # pairs follows on the same second stream.  (Splitting the batch in halves to overlap the stencils of one half
+        # with the tracker of the other was measured slower: the stencil CTAs queue behind the tracker's.)
+        main = torch.cuda.current_stream()
+        fork, pyr_done, join = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.stage_process(bgr)
+        fork.record(main)
+        with torch.cuda.stream(self.aux):
+            self.aux.wait_event(fork)
+            self.stage_refresh_detect()
         self.stage_pyramid()
-        self.stage_refresh()
-        self.stage_track()
+        pyr_done.record(main)
+        self.stage_track_main()
+        with torch.cuda.stream(self.aux):
+            self.aux.wait_event(pyr_done)
+            self.stage_track_refreshed()
+            join.record(self.aux)
+        main.wait_event(join)
         self.stage_carry()
 
     # -- CUDA graph ------------------------------------------------------------------------------
