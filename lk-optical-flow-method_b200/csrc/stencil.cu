@@ -347,24 +347,24 @@ bool stream_ok(const lkf_image *src, const lkf_image *dst)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pd_hsum_row(const uint8_t *__restrict__ row, int xs, int Ws, uint32_t (&h)[4])
 {
-    // source columns xs-2 .. xs+16 -> g[0..18]
-    uint32_t g[19];
+    // Packed form: E(w) = even columns of a word as two 16-bit lanes, O(w) = odd columns.  Output pair k (centres 4k, 4k+2):
+    //   (s[c-2] + s[c+2]) + 4 (s[c-1] + s[c+1]) + 6 s[c]  =  L2 + R2 + 4 (L1 + R1) + 6 C   with
+    //   C = E(w[k]), R1 = O(w[k]), L2 = (E(w[k-1]).hi, E(w[k]).lo), R2 = (E(w[k]).hi, E(w[k+1]).lo), L1 = (O(w[k-1]).hi, O(w[k]).lo).
     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + xs));
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t E[6], O[5];                       // E[k+1] = E(w[k]); E[0] / O[0]: left neighbour word, E[5]: right neighbour
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        g[4 * k + 2] = w[k] & 255u; g[4 * k + 3] = (w[k] >> 8) & 255u; g[4 * k + 4] = (w[k] >> 16) & 255u; g[4 * k + 5] = w[k] >> 24;
-    }
+    for (int k = 0; k < 4; k++) { E[k + 1] = w[k] & 0x00ff00ffu; O[k + 1] = (w[k] >> 8) & 0x00ff00ffu; }
     if (xs > 0) {
         const uint32_t l = __ldg(reinterpret_cast<const uint32_t *>(row + xs - 4));
-        g[0] = (l >> 16) & 255u; g[1] = l >> 24;
-    } else { g[0] = g[4]; g[1] = g[3]; }                                  // columns -2,-1 -> 2,1
-    g[18] = xs + 16 < Ws ? (uint32_t)__ldg(row + xs + 16) : g[16];          // column Ws -> Ws-2
+        E[0] = l & 0x00ff00ffu; O[0] = (l >> 8) & 0x00ff00ffu;
+    } else { E[0] = E[1]; O[0] = O[1] << 16; }                              // columns -2, -1 -> 2, 1
+    E[5] = xs + 16 < Ws ? (uint32_t)__ldg(row + xs + 16) : E[4] >> 16;       // column Ws -> Ws-2
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        uint32_t a = g[4 * k] + g[4 * k + 4] + 4u * (g[4 * k + 1] + g[4 * k + 3]) + 6u * g[4 * k + 2];
-        uint32_t b = g[4 * k + 2] + g[4 * k + 6] + 4u * (g[4 * k + 3] + g[4 * k + 5]) + 6u * g[4 * k + 4];
-        h[k] = a | (b << 16);
+        const uint32_t L2 = __byte_perm(E[k], E[k + 1], 0x5432), R2 = __byte_perm(E[k + 1], E[k + 2], 0x5432);
+        const uint32_t L1 = __byte_perm(O[k], O[k + 1], 0x5432);
+        h[k] = L2 + R2 + 4u * (L1 + O[k + 1]) + 6u * E[k + 1];
     }
 }
 
