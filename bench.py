@@ -334,6 +334,7 @@ def run_b200(args):
     stage_names = ["process_img", "pyramid", "gftt_refresh", "lk_track", "carry"]
     stage_fn = [lambda: pipe.stage_process(new_frames), pipe.stage_pyramid, pipe.stage_refresh,
                 lambda: pipe.stage_track(want_iters=False), pipe.stage_carry]
+    n_step_stages = len(stage_fn)
     pipe.set_points(pts)
     pipe.step(new_frames)                      # state every stage graph replays on: points after one refresh
     pipe.stage_track(want_iters=True)          # iteration counts for the op model (same points as the timed replays)
@@ -384,17 +385,19 @@ def run_b200(args):
     alg = {"process_img": B * 4.0 * P, "pyramid": B * pyr_bytes,
            "gftt_refresh": R * (5.0 * P + 9.0 * P), "carry": 2.0 * sum(P / 4 ** l for l in range(nl))}
     stages = {}
-    for n_, m_ in zip(stage_names, st_ms):
-        d = {"ms": float(m_), "share": float(m_ / st_ms.sum())}
+    step_sum = st_ms[:n_step_stages].sum()
+    for j_, (n_, m_) in enumerate(zip(stage_names, st_ms)):
+        d = {"ms": float(m_), "share": float(m_ / step_sum) if j_ < n_step_stages else None}
         if n_ in alg:
             d.update({"bound": "hbm", "algorithmic_bytes": alg[n_], "achieved_GBps": alg[n_] / (m_ * 1e-3) / 1e9,
                       "frac_of_hbm_peak": alg[n_] / (m_ * 1e-3) / 1e9 / hbm_peak})
         stages[n_] = d
     ops_lk = lk_ops(iters_total, n_tracked, nl, LK["winSize"])
-    lk_tflops = ops_lk / (st_ms[3] * 1e-3) / 1e12
+    lk_ms = st_ms[stage_names.index("lk_track")]
+    lk_tflops = ops_lk / (lk_ms * 1e-3) / 1e12
     stages["lk_track"].update({"bound": "fp32", "algorithmic_ops": ops_lk, "iterations_per_point": iters_total / max(1, n_tracked),
                                "achieved_TFLOPs": lk_tflops, "frac_of_fp32_peak": lk_tflops / fp32_peak})
-    dom = stage_names[int(np.argmax(st_ms))]
+    dom = stage_names[int(np.argmax(st_ms[:n_step_stages]))]
     if dom == "lk_track":
         roof = {"kernel": "k_lk_track_t<21,21>", "bound": "fp32", "achieved": lk_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": lk_tflops / fp32_peak,

@@ -90,6 +90,10 @@ int lkf_gaussian_blur3_u8(const lkf_image *src, const lkf_image *dst, lkf_stream
 int lkf_process_img_u8(const lkf_image *bgr, const lkf_image *dst, lkf_stream stream);
 /* ---- a3: one pyrDown step of the pyramid cv.calcOpticalFlowPyrLK builds   VP.py:545 -------- */
 int lkf_pyr_down_u8(const lkf_image *src, const lkf_image *dst, lkf_stream stream);
+/* ---- a1+a2+a3 for a whole pyramid (process_img VP.py:404-425 + the pyramid of VP.py:545): levels[0] = gray+blur of
+ *      `bgr`, levels[l] = pyrDown(levels[l-1]); `levels` is an array of n_levels descriptors (one call, the
+ *      per-level kernels back to back). */
+int lkf_process_pyramid_u8(const lkf_image *bgr, const lkf_image *levels, int n_levels, lkf_stream stream);
 /* ---- a4: Scharr Ix/Iy (int16 x2 interleaved) of one level, as PyrLK computes it  VP.py:545 -- */
 int lkf_scharr_s16(const lkf_image *src, const lkf_image *dst_ixiy, lkf_stream stream);
 /* levels cv2 really uses for a WxH image (maxLevel is reduced when a level would be <= winSize) */

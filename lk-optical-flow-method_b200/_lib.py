@@ -77,6 +77,7 @@ SIGNATURES = {
     "lkf_gaussian_blur3_u8": (_i, [_P(LkfImage), _P(LkfImage), _vp]),
     "lkf_process_img_u8": (_i, [_P(LkfImage), _P(LkfImage), _vp]),
     "lkf_pyr_down_u8": (_i, [_P(LkfImage), _P(LkfImage), _vp]),
+    "lkf_process_pyramid_u8": (_i, [_P(LkfImage), _P(LkfImage), ctypes.c_int, _vp]),
     "lkf_scharr_s16": (_i, [_P(LkfImage), _P(LkfImage), _vp]),
     "lkf_effective_max_level": (_i, [_i, _i, _i, _i, _i]),
     "lkf_pyrlk_sparse": (_i, [_vp, _P(LkfLkParams), _i, _P(LkfImage), _P(LkfImage), _vp, _vp, _i,

@@ -232,19 +232,14 @@ __global__ void __launch_bounds__(NT) k_scharr(SrcU8 src0, long long src_ip, Img
 // ---------------------------------------------------------------------------------------------
 constexpr int SV_NT = 128, SV_PX = 16;
 
-// (3735, 19235, 9798) = 128*(29, 150, 76) + (23, 35, 70); byte k of a word multiplies byte k of the weights
-__device__ __forceinline__ uint32_t gray_dp(uint32_t pix_lo3)
-{   // B,G,R in bytes 0,1,2 (byte 3 ignored)
-    const uint32_t WH = 29u | (150u << 8) | (76u << 16), WL = 23u | (35u << 8) | (70u << 16);
-    uint32_t lo = __dp4a(pix_lo3, WL, 16384u), hi = __dp4a(pix_lo3, WH, 0u);
-    return (lo + (hi << 7)) >> 15;
-}
-__device__ __forceinline__ uint32_t gray_dp_hi3(uint32_t pix_hi3)
-{   // B,G,R in bytes 1,2,3 (byte 0 ignored)
-    const uint32_t WH = (29u << 8) | (150u << 16) | (76u << 24), WL = (23u << 8) | (35u << 16) | (70u << 24);
-    uint32_t lo = __dp4a(pix_hi3, WL, 16384u), hi = __dp4a(pix_hi3, WH, 0u);
-    return (lo + (hi << 7)) >> 15;
-}
+// Gray of interleaved BGR with DP2A (two 16-bit weights x two bytes per instruction): the four pixels of three words
+// a = B0 G0 R0 B1 | b = G1 R1 B2 G2 | c = R2 B3 G3 R3 need no byte shuffling at all -- every pixel is one .lo and one .hi
+// dot product with one of four constant weight pairs.  Y = (3735 B + 19235 G + 9798 R + 2^14) >> 15.
+constexpr uint32_t GW_BG = 3735u | (19235u << 16), GW_R_ = 9798u, GW__B = 3735u << 16, GW_GR = 19235u | (9798u << 16);
+__device__ __forceinline__ uint32_t gray_px0(uint32_t a) { return __dp2a_hi(GW_R_, a, __dp2a_lo(GW_BG, a, 16384u)) >> 15; }             // bytes 0,1,2 of a
+__device__ __forceinline__ uint32_t gray_px1(uint32_t a, uint32_t b) { return __dp2a_lo(GW_GR, b, __dp2a_hi(GW__B, a, 16384u)) >> 15; } // a3 b0 b1
+__device__ __forceinline__ uint32_t gray_px2(uint32_t b, uint32_t c) { return __dp2a_lo(GW_R_, c, __dp2a_hi(GW_BG, b, 16384u)) >> 15; } // b2 b3 c0
+__device__ __forceinline__ uint32_t gray_px3(uint32_t c) { return __dp2a_hi(GW_GR, c, __dp2a_lo(GW__B, c, 16384u)) >> 15; }             // bytes 1,2,3 of c
 
 // 16 gray values of columns x0..x0+15 plus the neighbours g[-1], g[16]; g as 18 ints (index j+1)
 struct RowBGR {
@@ -256,14 +251,14 @@ struct RowBGR {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint32_t a = w[3 * k], b = w[3 * k + 1], c = w[3 * k + 2];
-            g[4 * k + 1] = gray_dp(a);                                   // bytes 0..2 of a
-            g[4 * k + 2] = gray_dp(__byte_perm(a, b, 0x0543));           // a3 b0 b1
-            g[4 * k + 3] = gray_dp(__byte_perm(b, c, 0x0432));           // b2 b3 c0
-            g[4 * k + 4] = gray_dp_hi3(c);                               // bytes 1..3 of c
+            g[4 * k + 1] = gray_px0(a);
+            g[4 * k + 2] = gray_px1(a, b);
+            g[4 * k + 3] = gray_px2(b, c);
+            g[4 * k + 4] = gray_px3(c);
         }
-        if (x0 > 0) g[0] = gray_dp_hi3(__ldg(reinterpret_cast<const uint32_t *>(row + 3 * x0 - 4)));
+        if (x0 > 0) g[0] = gray_px3(__ldg(reinterpret_cast<const uint32_t *>(row + 3 * x0 - 4)));
         else g[0] = g[2];                                                // REFLECT_101: column -1 -> 1
-        if (x0 + SV_PX < W) g[17] = gray_dp(__ldg(reinterpret_cast<const uint32_t *>(row + 3 * x0 + 48)));
+        if (x0 + SV_PX < W) g[17] = gray_px0(__ldg(reinterpret_cast<const uint32_t *>(row + 3 * x0 + 48)));
         else g[17] = g[15];                                              // column W -> W-2
     }
 };
@@ -486,4 +481,22 @@ LKF_EXPORT int lkf_effective_max_level(int height, int width, int win_w, int win
         if (w <= win_w || h <= win_h) return level;
     }
     return max_level;
+}
+
+/* a1+a2+a3 for a whole pyramid: levels[0] = process_img(bgr), levels[l] = pyrDown(levels[l-1]) -- one ABI call, the
+ * streaming kernels back to back.  (A single fused pass -- warp-sliding, all three levels in registers -- was built and
+ * measured in round 1: bit-exact but SLOWER, 200 us vs 108 + 76 us per 64 frames, because process_img is already
+ * issue-bound on B200 (18 instructions per pixel at 4.9 TB/s) and the halo rows/lanes of the fused form add more
+ * instructions than the saved 1.25 P of traffic is worth.) */
+LKF_EXPORT int lkf_process_pyramid_u8(const lkf_image *bgr, const lkf_image *levels, int n_levels, lkf_stream stream)
+{
+    if (!bgr || !levels || n_levels < 1 || n_levels > LKF_MAX_LEVELS) return LKF_ERR_ARG;
+    if (!img_ok(bgr, 3, 1) || !img_ok(&levels[0], 1, 1) || !same_geometry(bgr, &levels[0])) return LKF_ERR_ARG;
+    for (int l = 1; l < n_levels; l++)
+        if (!img_ok(&levels[l], 1, 1) || levels[l].batch != bgr->batch || levels[l].height != (levels[l - 1].height + 1) / 2 ||
+            levels[l].width != (levels[l - 1].width + 1) / 2)
+            return LKF_ERR_ARG;
+    int rc = lkf_process_img_u8(bgr, &levels[0], stream);
+    for (int l = 1; l < n_levels && rc == LKF_OK; l++) rc = lkf_pyr_down_u8(&levels[l - 1], &levels[l], stream);
+    return rc;
 }

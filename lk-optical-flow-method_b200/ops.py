@@ -66,6 +66,18 @@ def pyr_down(gray, out=None):
     return out
 
 
+def process_pyramid(bgr, out_levels):
+    """a1+a2+a3: out_levels[0] = process_img(bgr), out_levels[l] = pyrDown(out_levels[l-1]) (one ABI call)."""
+    ws = Workspace.current()
+    b4 = bgr if bgr.dim() == 4 else bgr.unsqueeze(0)
+    n = len(out_levels)
+    Arr = LkfImage * n
+    la = Arr(*[image_desc(_b3(t)) for t in out_levels])
+    s = image_desc(b4, 3)
+    check(ws.lib.lkf_process_pyramid_u8(ctypes.byref(s), la, n, stream_ptr()), "lkf_process_pyramid_u8")
+    return out_levels
+
+
 def effective_levels(H, W, win, max_level):
     """Number of pyramid levels cv2 uses (maxLevel+1 unless a level would be <= winSize)."""
     return _lib.load().lkf_effective_max_level(int(H), int(W), int(win[0]), int(win[1]), int(max_level)) + 1

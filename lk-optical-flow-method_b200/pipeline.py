@@ -104,6 +104,10 @@ class PairPipeline:
         for lv in self.levels:
             lv[0].copy_(lv[self.B])
 
+    def stage_process_pyramid(self, bgr):
+        """process_img + the whole pyramid of the B new frames in one ABI call."""
+        ops.process_pyramid(bgr, [lv[1:] for lv in self.levels])
+
     def stage_track_main(self, lo=0, hi=None):
         """LK of pairs lo..hi-1 that are NOT refreshed in this step (point count 0 for the refreshed ones)."""
         hi = self.B if hi is None else hi
@@ -135,30 +139,24 @@ class PairPipeline:
     def step(self, bgr):
         """bgr: [B,H,W,3] uint8 CUDA tensor = the B new frames of this step."""
         if not (self.R and self.overlap):
-            self.stage_process(bgr)
-            self.stage_pyramid()
+            self.stage_process_pyramid(bgr)
             self.stage_refresh()
             self.stage_track()
             self.stage_carry()
             return
-        # Fork: the refresh chain only needs level 0, so it starts next to the pyramid build and its one-CTA-per-image
-        # sort/selection is already resident when the main LK launch fills the machine; the LK launch of the refreshed
-        # pairs follows on the same second stream.  (Splitting the batch in halves to overlap the stencils of one half
+        # Fork after the stencil pass: the refresh chain and the LK launch of the refreshed pairs run on the
+        # second stream next to the main LK launch (the one-CTA-per-image sort/selection is latency-bound).  (Splitting the batch in halves to overlap the stencils of one half
         # with the tracker of the other was measured slower: the stencil CTAs queue behind the tracker's.)
         main = torch.cuda.current_stream()
-        fork, pyr_done, join = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-        self.stage_process(bgr)
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        self.stage_process_pyramid(bgr)
         fork.record(main)
         with torch.cuda.stream(self.aux):
             self.aux.wait_event(fork)
             self.stage_refresh_detect()
-        self.stage_pyramid()
-        pyr_done.record(main)
-        self.stage_track_main()
-        with torch.cuda.stream(self.aux):
-            self.aux.wait_event(pyr_done)
             self.stage_track_refreshed()
             join.record(self.aux)
+        self.stage_track_main()
         main.wait_event(join)
         self.stage_carry()
 

@@ -44,6 +44,31 @@ def test_gray_blur_pyr_scharr_bit_exact(oracle, W, H):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("W,H,levels", [(1920, 1080, 3), (960, 540, 3), (480, 16, 3), (1440, 36, 3), (3840, 2160, 3),
+                                        (1920, 1080, 4), (860, 483, 3), (960, 542, 3), (67, 35, 2)])
+def test_process_pyramid_bit_exact(oracle, W, H, levels):
+    """lkf_process_pyramid_u8: process_img + the whole pyramid in one ABI call -- every level bit-exact against the oracle,
+    including the mirrored borders of every level and the seams between thread strips."""
+    import torch
+    from lk_optical_flow_method_b200 import ops
+    from lk_optical_flow_method_b200.device import pyramid_shapes
+    rng = np.random.default_rng(W + 3 * H)
+    bgr = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+    if W >= 64 and W * H <= 1920 * 1080:
+        bgr[1] = synth_frames(W, H, 1)[0]
+    d = _dev(bgr)
+    outs = [torch.full((2, h, w), 7, dtype=torch.uint8, device="cuda") for (h, w) in pyramid_shapes(H, W, levels)]
+    ops.process_pyramid(d, outs)
+    ref = [np.stack([oracle.blur3(oracle.bgr2gray(f)) for f in bgr])]
+    for l in range(1, levels):
+        ref.append(np.stack([oracle.pyrdown(g) for g in ref[-1]]))
+    for l in range(levels):
+        got = outs[l].cpu().numpy()
+        assert got.shape == ref[l].shape
+        bad = np.argwhere(got != ref[l])
+        assert len(bad) == 0, (l, len(bad), bad[:5])
+
+
 def test_unaligned_views(oracle):
     """Row pitch / base pointers that are not 4- or 16-byte aligned take the scalar paths."""
     from lk_optical_flow_method_b200 import ops
