@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round evidence capture on the GPU box (one B200): tests, bench (both arms), ncu launch list, ncu --set full of the
-# step's kernels.  Outputs under gpurun_out/ (scratch); summaries are copied to profiles/ by tools/ncu_summary.py.
+# step's kernels (--launch-skip 44: 36 launches of input generation + priming, 8 of the first warm-up step).  Outputs under gpurun_out/ (scratch); summaries are copied to profiles/ by tools/ncu_summary.py.
 set -u
 TAG=${1:-r01}
 mkdir -p gpurun_out
@@ -9,6 +9,6 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -2 gpurun_out/${TAG}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:^k_ --launch-skip 12 -c 14 -o gpurun_out/${TAG}_full \
+ncu --set full --clock-control none --import-source on -k regex:^k_ --launch-skip 44 -c 8 -f -o gpurun_out/${TAG}_full \
     python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "full rc=$?"
 ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv
