@@ -12,6 +12,7 @@
 //      so they follow cv2's float32 sequence; only the (exact) integer sums replace cv2's float32
 //      lane accumulation (difference <= 3e-4 px, see tests).
 #include "common.cuh"
+#include <limits.h>
 
 namespace {
 
@@ -798,7 +799,7 @@ __device__ __forceinline__ void load_row_bytes(const uint8_t *__restrict__ P, lo
                                                uint32_t (&w)[(NB + 3) / 4])
 {
     constexpr int NW = (NB + 3) / 4;
-    const uint8_t *row = P + (long long)reflect101(gy, H) * rp;
+    const uint8_t *row = P + (long long)((unsigned)gy < (unsigned)H ? gy : reflect101(gy, H)) * rp;
     const int ax = (gx >> 2) << 2;
     if (al4 && ax >= 0 && ax + 4 * (NW + 1) <= W) {
         const uint32_t *q = reinterpret_cast<const uint32_t *>(row + ax);
@@ -818,7 +819,8 @@ __device__ __forceinline__ void load_row_bytes(const uint8_t *__restrict__ P, lo
 template <int NW>
 __device__ __forceinline__ int byte_of(const uint32_t (&w)[NW], int c) { return (int)((w[c >> 2] >> (8 * (c & 3))) & 255u); }
 
-// bilinear Q14 sums of N pixels from two packed byte rows: v[t] = top(t) w00 + top(t+1) w01 + bot(t) w10 + bot(t+1) w11
+// bilinear Q14 sums of N pixels from two packed byte rows: v[t] = top(t) w00 + top(t+1) w01 + bot(t) w10 + bot(t+1) w11,
+// rounded and shifted to I*32 ((sum + 2^8) >> 9)
 template <int N, int NW>
 __device__ __forceinline__ void bilinear_packed(const uint32_t (&top)[NW], const uint32_t (&bot)[NW], int first, int wT, int wB,
                                                 int (&v)[N])
@@ -831,8 +833,8 @@ __device__ __forceinline__ void bilinear_packed(const uint32_t (&top)[NW], const
             wa = i + 1 < NW ? __funnelshift_r(top[i], top[i + 1], 8) : top[i] >> 8;
             wc = i + 1 < NW ? __funnelshift_r(bot[i], bot[i + 1], 8) : bot[i] >> 8;
         } else { wa = top[i]; wc = bot[i]; }
-        int acc = (j & 2) ? dp2a_hi(wT, wa, 0) : dp2a_lo(wT, wa, 0);
-        v[t] = (j & 2) ? dp2a_hi(wB, wc, acc) : dp2a_lo(wB, wc, acc);
+        int acc = (j & 2) ? dp2a_hi(wT, wa, 256) : dp2a_lo(wT, wa, 256);
+        v[t] = ((j & 2) ? dp2a_hi(wB, wc, acc) : dp2a_lo(wB, wc, acc)) >> 9;
     }
 }
 
@@ -915,7 +917,7 @@ k_lk_track_small(LKLevels lv, int n_levels, int max_count, double eps2, int flag
                         bilinear_packed<WW, NWR>(raw[(y + 1) % 3], raw[(y + 2) % 3], 1, wT, wB, iv);
 #pragma unroll
                         for (int x = 0; x < WW; x++) {
-                            const int ivv = descale(iv[x], 9);
+                            const int ivv = iv[x];
                             const int ixv = descale(dIx[y & 1][x] * w00 + dIx[y & 1][x + 1] * w01 + dIx[(y + 1) & 1][x] * w10 +
                                                     dIx[(y + 1) & 1][x + 1] * w11, 14);
                             const int iyv = descale(dIy[y & 1][x] * w00 + dIy[y & 1][x + 1] * w01 + dIy[(y + 1) & 1][x] * w10 +
@@ -944,22 +946,26 @@ k_lk_track_small(LKLevels lv, int n_levels, int max_count, double eps2, int flag
         float pdx = 0.f, pdy = 0.f;
 
         // J - I~ over the window at integer origin (ix, iy) with the current weights; f(idx, diff)
+        // the (WW+1)x(WH+1) bytes of `next` under the window stay in registers while the integer origin does not move
+        // (after the first step of a level most iterations only change the sub-pixel weights)
+        uint32_t jrows[WH + 1][NWJ];
+        int jx = INT_MIN, jy = INT_MIN;
         auto sweep = [&](int ix, int iy, auto f) {
-            uint32_t top[NWJ], bot[NWJ];
-            load_row_bytes<WW + 1>(J, jrp, W, H, jal4, ix, iy, top);
+            if (ix != jx || iy != jy) {
+#pragma unroll
+                for (int y = 0; y <= WH; y++) load_row_bytes<WW + 1>(J, jrp, W, H, jal4, ix, iy + y, jrows[y]);
+                jx = ix; jy = iy;
+            }
 #pragma unroll
             for (int y = 0; y < WH; y++) {
-                load_row_bytes<WW + 1>(J, jrp, W, H, jal4, ix, iy + y + 1, bot);
                 int v[WW];
-                bilinear_packed<WW, NWJ>(top, bot, 0, wT, wB, v);
+                bilinear_packed<WW, NWJ>(jrows[y], jrows[y + 1], 0, wT, wB, v);
 #pragma unroll
                 for (int x = 0; x < WW; x++) {
                     const int idx = y * WW + x;
                     const int iv = (idx & 1) ? (int)(tI[idx / 2] >> 16) : (int)(tI[idx / 2] & 0xffffu);
-                    f(idx, descale(v[x], 9) - iv);
+                    f(idx, v[x] - iv);
                 }
-#pragma unroll
-                for (int i = 0; i < NWJ; i++) top[i] = bot[i];
             }
         };
 

@@ -31,6 +31,15 @@ elif op == "lk":
     pipe.set_points(cor, cnt)
     for _ in range(3):
         pipe.stage_track()
+elif op == "dense":
+    LK = dict(winSize=(5, 5), maxLevel=2, criteria=(3, 10, 0.03))
+    nl = ops.effective_levels(H, W, LK["winSize"], LK["maxLevel"])
+    pyr = ops.build_pyramid(gray[:2], nl)
+    ys, xs = torch.meshgrid(torch.arange(H, device="cuda"), torch.arange(W, device="cuda"), indexing="ij")
+    pts = torch.stack([xs.reshape(-1), ys.reshape(-1)], 1).float()[None].contiguous()
+    params = ops.lk_params_struct(**LK)
+    for _ in range(3):
+        ops.pyrlk([p[:1] for p in pyr], [p[1:2] for p in pyr], pts, params)
 elif op == "pyrdown":
     for _ in range(3):
         l1 = ops.pyr_down(gray)
