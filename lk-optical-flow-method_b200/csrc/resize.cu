@@ -32,6 +32,53 @@ k_resize_area(const uint8_t *__restrict__ src, long long srp, long long sip, int
     }
 }
 
+// Fast form for 3-channel frames whose horizontal footprint is at most 4 source pixels (scale < 3, e.g. 1920 -> 860 and
+// 1280 -> 860): one thread per destination pixel, all three channels at once (three independent accumulation chains),
+// the pixel's table entries held in registers, exact u8 -> f32 by bit pattern.  Same float32 operation order as above.
+__device__ __forceinline__ float u8_to_f32(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
+
+__global__ void __launch_bounds__(256)
+k_resize_area_bgr4(const uint8_t *__restrict__ src, long long srp, long long sip, uint8_t *__restrict__ dst, long long drp,
+                   long long dip, int Hd, int Wd, const int *__restrict__ xofs, const int *__restrict__ xsi,
+                   const float *__restrict__ xal, const int *__restrict__ yofs, const int *__restrict__ ysi,
+                   const float *__restrict__ yal)
+{
+    const int dx = blockIdx.x * 64 + (threadIdx.x & 63), dy = blockIdx.y * 4 + (threadIdx.x >> 6), b = blockIdx.z;
+    if (dx >= Wd || dy >= Hd) return;
+    const uint8_t *S = src + (long long)b * sip;
+    const int x0 = __ldg(xofs + dx), nx = __ldg(xofs + dx + 1) - x0, y0 = __ldg(yofs + dy), y1 = __ldg(yofs + dy + 1);
+    int xo[4];
+    float xa[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool on = k < nx;
+        xo[k] = on ? 3 * __ldg(xsi + x0 + k) : 0;
+        xa[k] = on ? __ldg(xal + x0 + k) : 0.f;
+    }
+    float sb = 0.f, sg = 0.f, sr = 0.f;
+    for (int j = y0; j < y1; j++) {
+        const uint8_t *row = S + (long long)__ldg(ysi + j) * srp;
+        const float ya = __ldg(yal + j);
+        float bb = 0.f, bg = 0.f, br = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < nx) {
+                const uint8_t *p = row + xo[k];
+                bb = __fadd_rn(bb, __fmul_rn(u8_to_f32(p[0]), xa[k]));
+                bg = __fadd_rn(bg, __fmul_rn(u8_to_f32(p[1]), xa[k]));
+                br = __fadd_rn(br, __fmul_rn(u8_to_f32(p[2]), xa[k]));
+            }
+        const float tb = __fmul_rn(ya, bb), tg = __fmul_rn(ya, bg), tr = __fmul_rn(ya, br);
+        if (j == y0) { sb = tb; sg = tg; sr = tr; }
+        else { sb = __fadd_rn(sb, tb); sg = __fadd_rn(sg, tg); sr = __fadd_rn(sr, tr); }
+    }
+    uint8_t *o = dst + (long long)b * dip + (long long)dy * drp + 3 * dx;
+    const float rb = rintf(sb), rg = rintf(sg), rr = rintf(sr);
+    o[0] = (uint8_t)(rb < 0.f ? 0.f : (rb > 255.f ? 255.f : rb));
+    o[1] = (uint8_t)(rg < 0.f ? 0.f : (rg > 255.f ? 255.f : rg));
+    o[2] = (uint8_t)(rr < 0.f ? 0.f : (rr > 255.f ? 255.f : rr));
+}
+
 }  // namespace
 
 LKF_EXPORT int lkf_resize_area_u8(const lkf_image *src, const lkf_image *dst, const int32_t *xofs, const int32_t *xsi,
@@ -45,6 +92,14 @@ LKF_EXPORT int lkf_resize_area_u8(const lkf_image *src, const lkf_image *dst, co
     if (dst->width >= src->width || dst->height >= src->height) return LKF_ERR_UNSUPPORTED;      // area DOWN-scaling only
     if (src->width % dst->width == 0 && src->height % dst->height == 0) return LKF_ERR_UNSUPPORTED;  // cv2's integer fast path
     dim3 grid((dst->width + 63) / 64, (dst->height + 3) / 4, dst->batch);
+    // horizontal footprint of a destination pixel: at most floor(scale) + 2 table entries
+    if (src->channels == 3 && 2LL * src->width < 5LL * dst->width) {      // scale < 2.5 -> at most 4 table entries per pixel
+        k_resize_area_bgr4<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch,
+                                                                  (uint8_t *)dst->data, dst->row_pitch, dst->image_pitch, dst->height,
+                                                                  dst->width, xofs, xsi, xalpha, yofs, ysi, yalpha);
+        LKF_LAUNCH_CHECK(nullptr);
+        return LKF_OK;
+    }
     k_resize_area<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch, src->channels,
                                                          (uint8_t *)dst->data, dst->row_pitch, dst->image_pitch, dst->height,
                                                          dst->width, xofs, xsi, xalpha, yofs, ysi, yalpha);

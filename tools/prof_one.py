@@ -31,6 +31,9 @@ elif op == "lk":
     pipe.set_points(cor, cnt)
     for _ in range(3):
         pipe.stage_track()
+elif op == "resize":
+    for _ in range(3):
+        r = ops.resize_area(frames, (860, 483))
 elif op == "dense":
     LK = dict(winSize=(5, 5), maxLevel=2, criteria=(3, 10, 0.03))
     nl = ops.effective_levels(H, W, LK["winSize"], LK["maxLevel"])
