@@ -125,7 +125,7 @@ struct MaskSet {
 constexpr int MES_WARPS = 2, MES_COLS = 120, MES_PF = 3;
 template <int BS> struct MES {
     static constexpr int R = BS / 2, RING = 2 * R + 1;
-    static constexpr size_t SMEM_PER_WARP = (size_t)RING * 3 * 128 * sizeof(double);
+    static constexpr size_t SMEM_PER_WARP = (size_t)RING * 3 * 128 * sizeof(float);
     static constexpr size_t SMEM = MES_WARPS * SMEM_PER_WARP;
 };
 
@@ -156,8 +156,8 @@ mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp,
     const bool valid = cx >= 0 && cx < W;
     const bool first = EDGE && cx == 0, last = EDGE && cx == W - 4;
     const bool emit = valid && lane >= 1 && lane <= 30;
-    // ring[slot][ch][half][lane]: a lane's two 16-byte halves sit in two lane-contiguous planes (conflict-free 128-bit access)
-    double *ring = reinterpret_cast<double *>(mes_smem + (size_t)warp * MES<BS>::SMEM_PER_WARP) + 2 * lane;
+    // ring[slot][ch][lane]: the float32 products of the last 2R+1 rows, one float4 per lane (conflict-free 128-bit access)
+    float4 *ring = reinterpret_cast<float4 *>(mes_smem + (size_t)warp * MES<BS>::SMEM_PER_WARP) + lane;
     const uint8_t *img = src + (long long)b * ip + (valid ? cx : 0);
     const int y0 = blockIdx.y * rows_per_strip, y1 = min(H, y0 + rows_per_strip);
     bool tl[4];
@@ -183,11 +183,11 @@ mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp,
                 rs[j] = __fadd_rn(__fadd_rn(__fmul_rn(s, f[j]), __fmul_rn(s2, f[j + 1])), __fmul_rn(s, f[j + 2]));
         }
     };
-    // horizontal FP64 box sums of one float32 product plane row (the lane's 4 columns)
-    auto hbox = [&](const float (&p)[4], double (&h)[4]) {
+    // horizontal FP64 box sums of the lane's 4 columns of one plane of vertical sums (neighbour columns by shuffle)
+    auto hbox = [&](const double (&p)[4], double (&h)[4]) {
         double v[10];
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[3 + j] = (double)p[j];
+        for (int j = 0; j < 4; j++) v[3 + j] = p[j];
 #pragma unroll
         for (int k = 1; k <= R; k++) {
             const double l = shfl_up_d(v[3 + 4 - k]);          // column -k   (left lane's column 4-k)
@@ -205,15 +205,11 @@ mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp,
             h[j] = acc;
         }
     };
-    auto ring_ld = [&](int row, int ch, double (&h)[4]) {
-        const double2 *q = reinterpret_cast<const double2 *>(ring + ((size_t)(row % RING) * 3 + ch) * 128);
-        const double2 a = q[0], c = q[32];
-        h[0] = a.x; h[1] = a.y; h[2] = c.x; h[3] = c.y;
+    auto ring_ld = [&](int row, int ch, float (&p)[4]) {
+        const float4 q = ring[((row % RING) * 3 + ch) * 32];
+        p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
     };
-    auto ring_st = [&](int row, int ch, const double (&h)[4]) {
-        double2 *q = reinterpret_cast<double2 *>(ring + ((size_t)(row % RING) * 3 + ch) * 128);
-        q[0] = make_double2(h[0], h[1]); q[32] = make_double2(h[2], h[3]);
-    };
+    auto ring_st = [&](int row, int ch, const float (&p)[4]) { ring[((row % RING) * 3 + ch) * 32] = make_float4(p[0], p[1], p[2], p[3]); };
     // fused a6 step 1: masked maximum of the map per (image, mask) as order-preserving keys (values are >= 0)
     unsigned best[MAXM];
 #pragma unroll
@@ -257,35 +253,40 @@ mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp,
 #pragma unroll
     for (int k = 0; k < MES_PF; k++) pf[k] = load_word(min(ylo + 1 + k, yhi + 1));
 
+    // Vertical FP64 running sums of the products per column (every term is a float32 product: the sums are exact and
+    // order-free), then the horizontal sums of those.  V of an output row: the first time the direct (mirrored) window sum
+    // from the ring, afterwards + entering row - leaving row.
     double vxx[4], vxy[4], vyy[4];
     bool have_v = false;
     int ynext = y0;
-    // V of output row y: first time the direct (mirrored) window sum from the ring, afterwards + entering - leaving row
-    auto advance = [&](int y, const double (&nxx)[4], const double (&nxy)[4], const double (&nyy)[4],
-                       const double (&oxx)[4], const double (&oxy)[4], const double (&oyy)[4]) {
+    auto advance = [&](int y, const float (&nxx)[4], const float (&nxy)[4], const float (&nyy)[4],
+                       const float (&oxx)[4], const float (&oxy)[4], const float (&oyy)[4]) {
         if (!have_v) {
 #pragma unroll
             for (int j = 0; j < 4; j++) { vxx[j] = 0.0; vxy[j] = 0.0; vyy[j] = 0.0; }
 #pragma unroll
             for (int k = -R; k <= R; k++) {
-                double hxx[4], hxy[4], hyy[4];
+                float qxx[4], qxy[4], qyy[4];
                 const int row = reflect101(y + k, H);
-                ring_ld(row, 0, hxx); ring_ld(row, 1, hxy); ring_ld(row, 2, hyy);
+                ring_ld(row, 0, qxx); ring_ld(row, 1, qxy); ring_ld(row, 2, qyy);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    vxx[j] = __dadd_rn(vxx[j], hxx[j]); vxy[j] = __dadd_rn(vxy[j], hxy[j]); vyy[j] = __dadd_rn(vyy[j], hyy[j]);
+                    vxx[j] = __dadd_rn(vxx[j], (double)qxx[j]); vxy[j] = __dadd_rn(vxy[j], (double)qxy[j]);
+                    vyy[j] = __dadd_rn(vyy[j], (double)qyy[j]);
                 }
             }
             have_v = true;
         } else {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                vxx[j] = __dsub_rn(__dadd_rn(vxx[j], nxx[j]), oxx[j]);
-                vxy[j] = __dsub_rn(__dadd_rn(vxy[j], nxy[j]), oxy[j]);
-                vyy[j] = __dsub_rn(__dadd_rn(vyy[j], nyy[j]), oyy[j]);
+                vxx[j] = __dsub_rn(__dadd_rn(vxx[j], (double)nxx[j]), (double)oxx[j]);
+                vxy[j] = __dsub_rn(__dadd_rn(vxy[j], (double)nxy[j]), (double)oxy[j]);
+                vyy[j] = __dsub_rn(__dadd_rn(vyy[j], (double)nyy[j]), (double)oyy[j]);
             }
         }
-        emit_row(y, vxx, vxy, vyy);
+        double hxx[4], hxy[4], hyy[4];
+        hbox(vxx, hxx); hbox(vxy, hxy); hbox(vyy, hyy);
+        emit_row(y, hxx, hxy, hyy);
     };
 
 #pragma unroll 1
@@ -296,7 +297,7 @@ mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp,
         pf[MES_PF - 1] = load_word(min(r + 1 + MES_PF, yhi + 1));
         float rd_p[4], rs_p[4];
         row_terms(w, rd_p, rs_p);
-        float pxx[4], pxy[4], pyy[4];
+        float pxx[4], pxy[4], pyy[4], oxx[4], oxy[4], oyy[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const float dx = __fmaf_rn(s, __fadd_rn(rd_m[j], rd_p[j]), __fmul_rn(s2, rd_c[j]));
@@ -304,25 +305,23 @@ mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp,
             pxx[j] = __fmul_rn(dx, dx); pxy[j] = __fmul_rn(dx, dy); pyy[j] = __fmul_rn(dy, dy);
             rd_m[j] = rd_c[j]; rd_c[j] = rd_p[j]; rs_m[j] = rs_c[j]; rs_c[j] = rs_p[j];
         }
-        double hxx[4], hxy[4], hyy[4], oxx[4], oxy[4], oyy[4];
-        hbox(pxx, hxx); hbox(pxy, hxy); hbox(pyy, hyy);
         const bool out = r - R == ynext;                    // warp-uniform
         if (out && have_v) {                                // leaving row: read before its slot is overwritten (RING = 2R+1)
             const int ro = reflect101(ynext - R - 1, H);
             ring_ld(ro, 0, oxx); ring_ld(ro, 1, oxy); ring_ld(ro, 2, oyy);
         }
-        ring_st(r, 0, hxx); ring_st(r, 1, hxy); ring_st(r, 2, hyy);
-        if (out) { advance(ynext, hxx, hxy, hyy, oxx, oxy, oyy); ynext++; }
+        ring_st(r, 0, pxx); ring_st(r, 1, pxy); ring_st(r, 2, pyy);
+        if (out) { advance(ynext, pxx, pxy, pyy, oxx, oxy, oyy); ynext++; }
     }
     // bottom of the image: the entering rows are mirrored rows that are still in the ring
     while (ynext < y1) {
-        double hxx[4], hxy[4], hyy[4], oxx[4], oxy[4], oyy[4];
+        float nxx[4], nxy[4], nyy[4], oxx[4], oxy[4], oyy[4];
         if (have_v) {
             const int rn = reflect101(ynext + R, H), ro = reflect101(ynext - R - 1, H);
-            ring_ld(rn, 0, hxx); ring_ld(rn, 1, hxy); ring_ld(rn, 2, hyy);
+            ring_ld(rn, 0, nxx); ring_ld(rn, 1, nxy); ring_ld(rn, 2, nyy);
             ring_ld(ro, 0, oxx); ring_ld(ro, 1, oxy); ring_ld(ro, 2, oyy);
         }
-        advance(ynext, hxx, hxy, hyy, oxx, oxy, oyy);
+        advance(ynext, nxx, nxy, nyy, oxx, oxy, oyy);
         ynext++;
     }
     if (maxkey) {
@@ -336,7 +335,7 @@ mes_body(unsigned char *mes_smem, const uint8_t *__restrict__ src, long long rp,
 }
 
 template <int BS>
-__global__ void __launch_bounds__(MES_WARPS * 32)
+__global__ void __launch_bounds__(MES_WARPS * 32, 8)
 k_min_eigen_stream(const uint8_t *__restrict__ src, long long rp, long long ip, int H, int W, float *__restrict__ dst,
                    long long drp, long long dip, int tail_cols, float s, float s2, int rows_per_strip, int dst_al16,
                    const int32_t *__restrict__ enable, MaskSet ms, int n_masks, unsigned *__restrict__ maxkey)
@@ -366,7 +365,7 @@ int launch_min_eigen_stream(lkf_ctx *ctx, const lkf_image *src, const lkf_image 
     // strip height: fill whole waves of resident CTAs (shared memory bounds residency), 8..64 rows per strip
     const int sms = ctx ? ctx->sm_count : 148;
     int per_sm = (int)((227 * 1024) / (MES<BS>::SMEM + 1024));
-    per_sm = per_sm > 6 ? 6 : per_sm;                         // ~160 registers x 64 threads: 6 CTAs
+    per_sm = per_sm > 8 ? 8 : per_sm;                         // registers: <= 8 CTAs of 64 threads
     const long long cap = (long long)sms * per_sm, col_ctas = (long long)ctas_x * B;
     const long long min_ctas = col_ctas * ((H + 63) / 64);
     const long long waves = (min_ctas + cap - 1) / cap;
