@@ -1075,11 +1075,11 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     }
     int rc = 1;
     if (p->win_w == 21 && p->win_h == 21)
-        rc = launch_lk_t<21, 21, 7, 6, 22, 52, 24>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<21, 21, 7, 1, 22, 28, 24>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 15 && p->win_h == 15)
-        rc = launch_lk_t<15, 15, 5, 6, 17, 36, 24>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<15, 15, 5, 1, 17, 24, 24>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 31 && p->win_h == 31)
-        rc = launch_lk_t<31, 31, 31, 6, 33, 52, 16>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<31, 31, 31, 1, 33, 44, 16>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 5 && p->win_h == 5)
         rc = launch_lk_small<5, 5>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 3 && p->win_h == 3)
