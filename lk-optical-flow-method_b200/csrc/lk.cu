@@ -41,6 +41,18 @@ __device__ __forceinline__ long long warp_sum(long long v)
     return v;
 }
 
+// cv2: delta.ddot(delta) <= epsilon, the dot product accumulated in double.  A float32 estimate decides all but the
+// borderline cases (relative error of the estimate < 3e-7), which take the exact double path.
+__device__ __forceinline__ bool lk_step_below_eps(float dx, float dy, double eps2)
+{
+    const float f = dx * dx + dy * dy, e = (float)eps2;
+    if (f < e * 0.999999f) return true;
+    if (f > e * 1.000001f) return false;
+    return __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2;
+}
+// cv2: std::abs(x) < 0.01 with a float x and the double constant 0.01: the largest float below 0.01 is fl(0.01)
+__device__ __forceinline__ bool lk_below_001(float x) { return fabsf(x) <= 0.00999999977648258209228515625f; }
+
 __device__ __forceinline__ void weights(float a, float b, int &w00, int &w01, int &w10, int &w11)
 {
     float na = __fsub_rn(1.f, a), nb = __fsub_rn(1.f, b);
@@ -221,8 +233,8 @@ k_lk_track(LKLevels lv, int n_levels, int w, int h, int max_count, double eps2, 
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
             npx = __fadd_rn(nx, hx); npy = __fadd_rn(ny, hy);
-            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2) break;
-            if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+            if (lk_step_below_eps(dx, dy, eps2)) break;
+            if (j > 0 && lk_below_001(__fadd_rn(dx, pdx)) && lk_below_001(__fadd_rn(dy, pdy))) {
                 npx = __fsub_rn(npx, __fmul_rn(dx, 0.5f));
                 npy = __fsub_rn(npy, __fmul_rn(dy, 0.5f));
                 break;
@@ -726,8 +738,8 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
             npx = __fadd_rn(nx, hx); npy = __fadd_rn(ny, hy);
-            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2) break;
-            if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+            if (lk_step_below_eps(dx, dy, eps2)) break;
+            if (j > 0 && lk_below_001(__fadd_rn(dx, pdx)) && lk_below_001(__fadd_rn(dy, pdy))) {
                 npx = __fsub_rn(npx, __fmul_rn(dx, 0.5f));
                 npy = __fsub_rn(npy, __fmul_rn(dy, 0.5f));
                 break;
@@ -985,8 +997,8 @@ k_lk_track_small(LKLevels lv, int n_levels, int max_count, double eps2, int flag
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
             npx = __fadd_rn(nx, hx); npy = __fadd_rn(ny, hy);
-            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2) break;
-            if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+            if (lk_step_below_eps(dx, dy, eps2)) break;
+            if (j > 0 && lk_below_001(__fadd_rn(dx, pdx)) && lk_below_001(__fadd_rn(dy, pdy))) {
                 npx = __fsub_rn(npx, __fmul_rn(dx, 0.5f));
                 npy = __fsub_rn(npy, __fmul_rn(dy, 0.5f));
                 break;
