@@ -290,6 +290,8 @@ struct LKT {
     static constexpr int TH = WH + 1 + 2 * MARGIN;
     // interior windows: U = Q14-weighted raw sums on the (WW+2)x(WH+2) grid, int32, pitch UP (bank-spread, 16-byte rows)
     static constexpr int USEG = (WW + 2 + 3) / 4, UP = 4 * USEG + ((4 * USEG) % 8 == 0 ? 4 : 0), UH = WH + 2;
+    static constexpr int USEG6 = (WW + 2 + 5) / 6;                    // U is produced in runs of 6 values (3 x 64-bit stores)
+    static_assert(6 * USEG6 <= UP && UP % 2 == 0, "U pitch");
     static constexpr int DER_ONLY = (DWP * DH * 4 + 15) & ~15, U_BYTES = (UP * UH * 4 + 15) & ~15;
     static constexpr int DER_BYTES = DER_ONLY > U_BYTES ? DER_ONLY : U_BYTES, TILE_BYTES = (TWC * TH + 15) & ~15;
     static constexpr int RAW_BYTES = ((RWP * RH + 15) & ~15) + 16;     // + slack: word loaders read up to 2 words past a run
@@ -596,11 +598,12 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
             //     I~ = (U + 2^8) >> 9.  U on the (WW+2)x(WH+2) grid: 2 DP2A per value (4 values per lane step).
             int *U = reinterpret_cast<int *>(der);
             const int wT = (w00 & 0xffff) | (w01 << 16), wB = (w10 & 0xffff) | (w11 << 16);
-            for (int sg = lane; sg < T::UH * T::USEG; sg += 32) {
-                const int row = sg / T::USEG, sx = (sg - row * T::USEG) * 4;
-                int u[4];
-                bilinear_run<4, false>(raw + row * T::RWP, raw + (row + 1) * T::RWP, ro + sx, wT, wB, u);
-                *reinterpret_cast<int4 *>(U + row * T::UP + sx) = make_int4(u[0], u[1], u[2], u[3]);
+            for (int sg = lane; sg < T::UH * T::USEG6; sg += 32) {
+                const int row = sg / T::USEG6, sx = (sg - row * T::USEG6) * 6;
+                int u[6];
+                bilinear_run<6, false>(raw + row * T::RWP, raw + (row + 1) * T::RWP, ro + sx, wT, wB, u);
+                int2 *o = reinterpret_cast<int2 *>(U + row * T::UP + sx);
+                o[0] = make_int2(u[0], u[1]); o[1] = make_int2(u[2], u[3]); o[2] = make_int2(u[4], u[5]);
             }
             __syncwarp();
             // 3a. template from U: window pixel (x, y) is U(x+1, y+1); its 3x3 Scharr support is U(x..x+2, y..y+2).
