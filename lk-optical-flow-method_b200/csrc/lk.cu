@@ -621,19 +621,22 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
                 int s11 = 0, s12 = 0, s22 = 0;
 #pragma unroll
                 for (int c0 = 0; c0 < RUN; c0 += CH) {
-                    int p0[CH + 2], p1[CH + 2], p2[CH + 2];
+                    // column terms first: V = [3 10 3] down the three rows, Dv = bottom - top; then Ix = V(x+2) - V(x) and
+                    // Iy = 3 Dv(x) + 10 Dv(x+1) + 3 Dv(x+2)
+                    int V[CH + 2], Dv[CH + 2], ctr[CH + 2];
 #pragma unroll
                     for (int i = 0; i < CH + 2; i++)
-                        if (c0 + i < RUN + 2) { p0[i] = u0[c0 + i]; p1[i] = u1[c0 + i]; p2[i] = u2[c0 + i]; }
+                        if (c0 + i < RUN + 2) {
+                            const int a = u0[c0 + i], m = u1[c0 + i], c = u2[c0 + i];
+                            V[i] = 3 * (a + c) + 10 * m; Dv[i] = c - a; ctr[i] = m;
+                        }
 #pragma unroll
                     for (int i = 0; i < CH; i++) {
                         if (c0 + i < RUN) {
                             const int t = c0 + i;
-                            const int d0 = p0[i + 2] - p0[i], d1 = p1[i + 2] - p1[i], d2 = p2[i + 2] - p2[i];
-                            const int s0 = 3 * (p0[i] + p0[i + 2]) + 10 * p0[i + 1], s2 = 3 * (p2[i] + p2[i + 2]) + 10 * p2[i + 1];
-                            const int ixv = (3 * (d0 + d2) + 10 * d1 + (1 << 13)) >> 14;
-                            const int iyv = (s2 - s0 + (1 << 13)) >> 14;
-                            const int iv = (p1[i + 1] + (1 << 8)) >> 9;
+                            const int ixv = (V[i + 2] - V[i] + (1 << 13)) >> 14;
+                            const int iyv = (3 * (Dv[i] + Dv[i + 2]) + 10 * Dv[i + 1] + (1 << 13)) >> 14;
+                            const int iv = (ctr[i + 1] + (1 << 8)) >> 9;
                             if (t & 1) wI[t / 2] |= (uint32_t)iv << 16; else wI[t / 2] = (uint32_t)iv;
                             wD[t] = ((uint32_t)ixv & 0xffffu) | ((uint32_t)iyv << 16);
                             s11 += ixv * ixv; s12 += ixv * iyv; s22 += iyv * iyv;
