@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(SV_NT) k_blur3_stream(const uint8_t *__restric
                                                         uint8_t *__restrict__ dst, long long drp, long long dip, int H, int W,
                                                         int rows_per_block)
 {
-    const int x0 = (blockIdx.x * SV_NT + threadIdx.x) * SV_PX;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * SV_PX;
     if (x0 >= W) return;
     const int b = blockIdx.z;
     const uint8_t *S = src + (long long)b * sip;
@@ -319,12 +319,20 @@ __global__ void __launch_bounds__(SV_NT) k_blur3_stream(const uint8_t *__restric
     }
 }
 
+// threads per CTA of the streaming kernels: the columns of one image row rounded up to whole warps, at most SV_NT
+static inline int stream_threads(int columns_of_threads)
+{
+    int nt = (columns_of_threads + 31) & ~31;
+    return nt < 32 ? 32 : (nt > SV_NT ? SV_NT : nt);
+}
+
 template <class Row>
 int launch_blur3_stream(const lkf_image *src, const lkf_image *dst, cudaStream_t s)
 {
     const int H = dst->height, W = dst->width, R = 32;
-    dim3 grid((W / SV_PX + SV_NT - 1) / SV_NT, (H + R - 1) / R, dst->batch);
-    k_blur3_stream<Row><<<grid, SV_NT, 0, s>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch, (uint8_t *)dst->data,
+    const int nt = stream_threads(W / SV_PX);                  // narrow images: smaller CTAs, no idle warps
+    dim3 grid((W / SV_PX + nt - 1) / nt, (H + R - 1) / R, dst->batch);
+    k_blur3_stream<Row><<<grid, nt, 0, s>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch, (uint8_t *)dst->data,
                                                dst->row_pitch, dst->image_pitch, H, W, R);
     return LKF_OK;
 }
@@ -367,7 +375,7 @@ __global__ void __launch_bounds__(SV_NT) k_pyrdown_stream(const uint8_t *__restr
                                                           uint8_t *__restrict__ dst, long long drp, long long dip, int Hs, int Ws,
                                                           int Hd, int Wd, int rows_per_block)
 {
-    const int xo = (blockIdx.x * SV_NT + threadIdx.x) * 8;
+    const int xo = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (xo >= Wd) return;
     const int b = blockIdx.z, xs = 2 * xo;
     const uint8_t *S = src + (long long)b * sip;
@@ -447,8 +455,9 @@ LKF_EXPORT int lkf_pyr_down_u8(const lkf_image *src, const lkf_image *dst, lkf_s
         return LKF_ERR_ARG;
     if (src->width % 16 == 0 && src->width >= 32 && src->height >= 4 && aligned_to(src, 16) && aligned_to(dst, 8)) {
         const int R = 16;
-        dim3 g((dst->width / 8 + SV_NT - 1) / SV_NT, (dst->height + R - 1) / R, dst->batch);
-        k_pyrdown_stream<<<g, SV_NT, 0, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch,
+        const int nt = stream_threads(dst->width / 8);
+        dim3 g((dst->width / 8 + nt - 1) / nt, (dst->height + R - 1) / R, dst->batch);
+        k_pyrdown_stream<<<g, nt, 0, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch,
                                                                 (uint8_t *)dst->data, dst->row_pitch, dst->image_pitch, src->height,
                                                                 src->width, dst->height, dst->width, R);
         LKF_LAUNCH_CHECK(nullptr);
