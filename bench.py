@@ -287,6 +287,31 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPUs next to its GPU (PCIe root / NUMA node) before the pinned host buffers are allocated, so
+    the H2D stream of the e2e arm does not cross sockets.  Best effort: silently does nothing where sysfs says nothing."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        addr = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{addr}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{addr}: cpus {spec}"
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -295,6 +320,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from lk_optical_flow_method_b200 import _lib, ops
@@ -469,7 +495,8 @@ def run_b200(args):
                            "timed": "CUDA-graph replay of the whole step, CUDA events on the launch stream"},
                 "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),
-                        "note": "pinned host BGR frames + points -> H2D -> kernels -> D2H tracks, double-buffered copy stream"},
+                        "note": "pinned host BGR frames + points -> H2D -> kernels -> D2H tracks, double-buffered copy stream",
+                        "cpu_binding_rank0": numa},
                 "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
                 "roofline": roof, "roofline_hbm_stencil": roof_hbm, "stages": stages,
                 "fp32_peak_tflops_measured": fp32_peak, "cpu_baseline": cpu, "clocks": clk}
