@@ -348,21 +348,31 @@ bool stream_ok(const lkf_image *src, const lkf_image *dst)
 // source row are packed two per register (<= 4080), five rows of them live in registers, and the
 // vertical pass + rounding run on the packed pairs (16*4080 + 128 < 2^16, no carry between halves).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pd_hsum_row(const uint8_t *__restrict__ row, int xs, int Ws, uint32_t (&h)[4])
+// raw bytes of one source row for a thread: 16 columns + the word left of them + the byte right of them
+struct PdRaw { uint4 v; uint32_t l, r; };
+__device__ __forceinline__ PdRaw pd_load_row(const uint8_t *__restrict__ S, long long srp, int y, int Hs, int xs, int Ws)
+{
+    if (y < 0) y = -y; else if (y >= Hs) y = 2 * (Hs - 1) - y;            // REFLECT_101, |overshoot| <= 2 < Hs
+    const uint8_t *row = S + (long long)y * srp;
+    PdRaw q;
+    q.v = __ldg(reinterpret_cast<const uint4 *>(row + xs));
+    q.l = xs > 0 ? __ldg(reinterpret_cast<const uint32_t *>(row + xs - 4)) : 0u;
+    q.r = xs + 16 < Ws ? (uint32_t)__ldg(row + xs + 16) : 0u;
+    return q;
+}
+
+__device__ __forceinline__ void pd_hsum_row(const PdRaw &q, int xs, int Ws, uint32_t (&h)[4])
 {
     // Packed form: E(w) = even columns of a word as two 16-bit lanes, O(w) = odd columns.  Output pair k (centres 4k, 4k+2):
     //   (s[c-2] + s[c+2]) + 4 (s[c-1] + s[c+1]) + 6 s[c]  =  L2 + R2 + 4 (L1 + R1) + 6 C   with
     //   C = E(w[k]), R1 = O(w[k]), L2 = (E(w[k-1]).hi, E(w[k]).lo), R2 = (E(w[k]).hi, E(w[k+1]).lo), L1 = (O(w[k-1]).hi, O(w[k]).lo).
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + xs));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t w[4] = {q.v.x, q.v.y, q.v.z, q.v.w};
     uint32_t E[6], O[5];                       // E[k+1] = E(w[k]); E[0] / O[0]: left neighbour word, E[5]: right neighbour
 #pragma unroll
     for (int k = 0; k < 4; k++) { E[k + 1] = w[k] & 0x00ff00ffu; O[k + 1] = (w[k] >> 8) & 0x00ff00ffu; }
-    if (xs > 0) {
-        const uint32_t l = __ldg(reinterpret_cast<const uint32_t *>(row + xs - 4));
-        E[0] = l & 0x00ff00ffu; O[0] = (l >> 8) & 0x00ff00ffu;
-    } else { E[0] = E[1]; O[0] = O[1] << 16; }                              // columns -2, -1 -> 2, 1
-    E[5] = xs + 16 < Ws ? (uint32_t)__ldg(row + xs + 16) : E[4] >> 16;       // column Ws -> Ws-2
+    if (xs > 0) { E[0] = q.l & 0x00ff00ffu; O[0] = (q.l >> 8) & 0x00ff00ffu; }
+    else { E[0] = E[1]; O[0] = O[1] << 16; }                                // columns -2, -1 -> 2, 1
+    E[5] = xs + 16 < Ws ? q.r : E[4] >> 16;                                  // column Ws -> Ws-2
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t L2 = __byte_perm(E[k], E[k + 1], 0x5432), R2 = __byte_perm(E[k + 1], E[k + 2], 0x5432);
@@ -382,12 +392,18 @@ __global__ void __launch_bounds__(SV_NT) k_pyrdown_stream(const uint8_t *__restr
     uint8_t *D = dst + (long long)b * dip + xo;
     const int y0 = blockIdx.y * rows_per_block, y1 = min(Hd, y0 + rows_per_block);
     uint32_t r0[4], r1[4], r2[4], r3[4], r4[4];
-    pd_hsum_row(S + (long long)reflect101(2 * y0 - 2, Hs) * srp, xs, Ws, r0);
-    pd_hsum_row(S + (long long)reflect101(2 * y0 - 1, Hs) * srp, xs, Ws, r1);
-    pd_hsum_row(S + (long long)reflect101(2 * y0, Hs) * srp, xs, Ws, r2);
+    {
+        const PdRaw q0 = pd_load_row(S, srp, 2 * y0 - 2, Hs, xs, Ws), q1 = pd_load_row(S, srp, 2 * y0 - 1, Hs, xs, Ws),
+                    q2 = pd_load_row(S, srp, 2 * y0, Hs, xs, Ws);
+        pd_hsum_row(q0, xs, Ws, r0); pd_hsum_row(q1, xs, Ws, r1); pd_hsum_row(q2, xs, Ws, r2);
+    }
+    // the two source rows of the next output row are loaded one iteration ahead (more bytes in flight per thread)
+    PdRaw na = pd_load_row(S, srp, 2 * y0 + 1, Hs, xs, Ws), nb = pd_load_row(S, srp, 2 * y0 + 2, Hs, xs, Ws);
     for (int y = y0; y < y1; y++) {
-        pd_hsum_row(S + (long long)reflect101(2 * y + 1, Hs) * srp, xs, Ws, r3);
-        pd_hsum_row(S + (long long)reflect101(2 * y + 2, Hs) * srp, xs, Ws, r4);
+        const PdRaw qa = na, qb = nb;
+        if (y + 1 < y1) { na = pd_load_row(S, srp, 2 * y + 3, Hs, xs, Ws); nb = pd_load_row(S, srp, 2 * y + 4, Hs, xs, Ws); }
+        pd_hsum_row(qa, xs, Ws, r3);
+        pd_hsum_row(qb, xs, Ws, r4);
         uint32_t o[4];
 #pragma unroll
         for (int k = 0; k < 4; k++)
