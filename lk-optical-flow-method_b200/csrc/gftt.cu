@@ -472,6 +472,8 @@ k_nms_compact(const float *__restrict__ eig, long long erp, long long eip, int H
 
 // Same selection, 4 pixels per thread (128-bit loads of the centre row; rows above / below only where a pixel survives the
 // weakest threshold).  Needs 16-byte aligned eig rows.  Candidate order inside a list is irrelevant (sorted afterwards).
+constexpr int NMS4_ROWS = 4;        // rows per thread (their centre loads are issued together: memory-level parallelism)
+
 __global__ void __launch_bounds__(256)
 k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int H, int W, MaskSet ms, int n_masks,
                const unsigned *__restrict__ maxkey, double quality, unsigned long long *__restrict__ keys,
@@ -481,7 +483,7 @@ k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int 
     if (enable && !enable[b]) return;
     const int lane = threadIdx.x & 31;
     const int x0 = (blockIdx.x * 32 + lane) * 4;
-    const int y = 1 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int ybase = 1 + blockIdx.y * (8 * NMS4_ROWS) + (threadIdx.x >> 5);
     const unsigned char *e = reinterpret_cast<const unsigned char *>(eig) + (long long)b * eip;
     float thr_m[MAXM], thr_min = 3.4e38f;
 #pragma unroll
@@ -491,63 +493,75 @@ k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int 
         thr_m[m] = (float)((mk ? (double)key2f(mk) : 0.0) * quality);
         thr_min = fminf(thr_min, thr_m[m]);
     }
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    bool is_max[4] = {false, false, false, false};
-    if (y < H - 1 && x0 < W) {
-        const float *r1 = reinterpret_cast<const float *>(e + (long long)y * erp) + x0;
-        float c[6];                                     // columns x0-1 .. x0+4 of the centre row
-        if (x0 + 3 < W) { const float4 q = *reinterpret_cast<const float4 *>(r1); c[1] = q.x; c[2] = q.y; c[3] = q.z; c[4] = q.w; }
-        else
-            for (int j = 0; j < 4; j++) c[1 + j] = x0 + j < W ? r1[j] : 0.f;
-        bool any = false;
+    const bool full = x0 + 3 < W;
+    float4 cq[NMS4_ROWS];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int x = x0 + j;
-            v[j] = c[1 + j];
-            any |= x >= 1 && x < W - 1 && v[j] > thr_min && v[j] != 0.f;
-        }
-        if (any) {
-            const float *r0 = reinterpret_cast<const float *>(e + (long long)(y - 1) * erp) + x0;
-            const float *r2 = reinterpret_cast<const float *>(e + (long long)(y + 1) * erp) + x0;
-            float a[6], d[6];
-            if (x0 + 3 < W) {
-                const float4 qa = *reinterpret_cast<const float4 *>(r0), qd = *reinterpret_cast<const float4 *>(r2);
-                a[1] = qa.x; a[2] = qa.y; a[3] = qa.z; a[4] = qa.w; d[1] = qd.x; d[2] = qd.y; d[3] = qd.z; d[4] = qd.w;
-            } else
-                for (int j = 0; j < 4; j++) { a[1 + j] = x0 + j < W ? r0[j] : 0.f; d[1 + j] = x0 + j < W ? r2[j] : 0.f; }
-            const bool hl = x0 > 0, hr = x0 + 4 < W;
-            a[0] = hl ? r0[-1] : 0.f; c[0] = hl ? r1[-1] : 0.f; d[0] = hl ? r2[-1] : 0.f;
-            a[5] = hr ? r0[4] : 0.f; c[5] = hr ? r1[4] : 0.f; d[5] = hr ? r2[4] : 0.f;
+    for (int r = 0; r < NMS4_ROWS; r++) {
+        const int y = ybase + 8 * r;
+        cq[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y < H - 1 && full) cq[r] = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(e + (long long)y * erp) + x0);
+    }
+#pragma unroll
+    for (int r = 0; r < NMS4_ROWS; r++) {
+        const int y = ybase + 8 * r;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        bool is_max[4] = {false, false, false, false};
+        if (y < H - 1 && x0 < W) {
+            const float *r1 = reinterpret_cast<const float *>(e + (long long)y * erp) + x0;
+            float c[6];                                     // columns x0-1 .. x0+4 of the centre row
+            if (full) { c[1] = cq[r].x; c[2] = cq[r].y; c[3] = cq[r].z; c[4] = cq[r].w; }
+            else
+                for (int j = 0; j < 4; j++) c[1 + j] = x0 + j < W ? r1[j] : 0.f;
+            bool any = false;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int x = x0 + j;
-                if (x >= 1 && x < W - 1 && v[j] > thr_min && v[j] != 0.f) {
-                    const float m = fmaxf(fmaxf(fmaxf(a[j], a[j + 1]), fmaxf(a[j + 2], c[j])), fmaxf(fmaxf(c[j + 2], d[j]), fmaxf(d[j + 1], d[j + 2])));
-                    is_max[j] = v[j] >= m;
+                v[j] = c[1 + j];
+                any |= x >= 1 && x < W - 1 && v[j] > thr_min && v[j] != 0.f;
+            }
+            if (any) {
+                const float *r0 = reinterpret_cast<const float *>(e + (long long)(y - 1) * erp) + x0;
+                const float *r2 = reinterpret_cast<const float *>(e + (long long)(y + 1) * erp) + x0;
+                float a[6], d[6];
+                if (full) {
+                    const float4 qa = *reinterpret_cast<const float4 *>(r0), qd = *reinterpret_cast<const float4 *>(r2);
+                    a[1] = qa.x; a[2] = qa.y; a[3] = qa.z; a[4] = qa.w; d[1] = qd.x; d[2] = qd.y; d[3] = qd.z; d[4] = qd.w;
+                } else
+                    for (int j = 0; j < 4; j++) { a[1 + j] = x0 + j < W ? r0[j] : 0.f; d[1 + j] = x0 + j < W ? r2[j] : 0.f; }
+                const bool hl = x0 > 0, hr = x0 + 4 < W;
+                a[0] = hl ? r0[-1] : 0.f; c[0] = hl ? r1[-1] : 0.f; d[0] = hl ? r2[-1] : 0.f;
+                a[5] = hr ? r0[4] : 0.f; c[5] = hr ? r1[4] : 0.f; d[5] = hr ? r2[4] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int x = x0 + j;
+                    if (x >= 1 && x < W - 1 && v[j] > thr_min && v[j] != 0.f) {
+                        const float m = fmaxf(fmaxf(fmaxf(a[j], a[j + 1]), fmaxf(a[j + 2], c[j])), fmaxf(fmaxf(c[j + 2], d[j]), fmaxf(d[j + 1], d[j + 2])));
+                        is_max[j] = v[j] >= m;
+                    }
                 }
             }
         }
-    }
-    if (!__any_sync(0xffffffffu, is_max[0] || is_max[1] || is_max[2] || is_max[3])) return;
+        if (!__any_sync(0xffffffffu, is_max[0] || is_max[1] || is_max[2] || is_max[3])) continue;
 #pragma unroll
-    for (int m = 0; m < MAXM; m++) {
-        if (m >= n_masks) break;
-        const int list = b * n_masks + m;
-        const float thr = thr_m[m];
+        for (int m = 0; m < MAXM; m++) {
+            if (m >= n_masks) break;
+            const int list = b * n_masks + m;
+            const float thr = thr_m[m];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int x = x0 + j;
-            bool cand = is_max[j] && v[j] > thr;
-            if (cand && ms.p) cand = ms.p[(long long)(ms.per_image ? list : m) * ms.ip + (long long)y * ms.rp + x] != 0;
-            const unsigned bal = __ballot_sync(0xffffffffu, cand);
-            if (bal) {
-                const int leader = __ffs(bal) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(&counts[list], __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (cand) {
-                    const int pos = base + __popc(bal & ((1u << lane) - 1));
-                    if (pos < cap) keys[(long long)list * cap + pos] = ((unsigned long long)f2key(v[j]) << 32) | (unsigned)(y * W + x);
+            for (int j = 0; j < 4; j++) {
+                const int x = x0 + j;
+                bool cand = is_max[j] && v[j] > thr;
+                if (cand && ms.p) cand = ms.p[(long long)(ms.per_image ? list : m) * ms.ip + (long long)y * ms.rp + x] != 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, cand);
+                if (bal) {
+                    const int leader = __ffs(bal) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&counts[list], __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (cand) {
+                        const int pos = base + __popc(bal & ((1u << lane) - 1));
+                        if (pos < cap) keys[(long long)list * cap + pos] = ((unsigned long long)f2key(v[j]) << 32) | (unsigned)(y * W + x);
+                    }
                 }
             }
         }
@@ -809,7 +823,7 @@ static int gftt_passes(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *
         LKF_LAUNCH_CHECK(ctx);
     }
     if (aligned_to(eig, 16)) {
-        dim3 g4((W + 127) / 128, (H - 2 + 7) / 8, B);
+        dim3 g4((W + 127) / 128, (H - 2 + 8 * NMS4_ROWS - 1) / (8 * NMS4_ROWS), B);
         k_nms_compact4<<<g4, 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, g.maxkey,
                                           p->quality_level, g.keys, g.ccount, g.cap, enable);
     } else {
