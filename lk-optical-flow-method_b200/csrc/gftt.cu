@@ -102,6 +102,15 @@ __device__ __forceinline__ float key2f(unsigned k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Candidate histogram (per list) over the order-preserving keys, counted from the list's maximum downwards: bin width 2^16
+// key units = 1/128 octave.  The selection kernel uses it to sort only the strongest candidates it can possibly need.
+constexpr int GF_BINS = 2048, GF_BIN_SHIFT = 16;
+__device__ __forceinline__ int key_bin(unsigned kmax, unsigned key)
+{
+    const unsigned d = (kmax - key) >> GF_BIN_SHIFT;
+    return d >= (unsigned)GF_BINS ? GF_BINS - 1 : (int)d;
+}
+
 constexpr int MAXM = 8;      // masks per image handled in one pass
 
 struct MaskSet {
@@ -417,7 +426,7 @@ k_masked_max(const float *__restrict__ eig, long long erp, long long eip, int H,
 __global__ void __launch_bounds__(256)
 k_nms_compact(const float *__restrict__ eig, long long erp, long long eip, int H, int W, MaskSet ms, int n_masks,
               const unsigned *__restrict__ maxkey, double quality, unsigned long long *__restrict__ keys,
-              int *__restrict__ counts, int cap, const int32_t *__restrict__ enable)
+              int *__restrict__ counts, int cap, const int32_t *__restrict__ enable, int *__restrict__ hist)
 {
     const int b = blockIdx.z;
     if (enable && !enable[b]) return;
@@ -465,6 +474,7 @@ k_nms_compact(const float *__restrict__ eig, long long erp, long long eip, int H
                 int pos = base + __popc(bal & ((1u << lane) - 1));
                 if (pos < cap)
                     keys[(long long)list * cap + pos] = ((unsigned long long)f2key(v) << 32) | (unsigned)(y * W + x);
+                atomicAdd(&hist[list * GF_BINS + key_bin(maxkey[list], f2key(v))], 1);
             }
         }
     }
@@ -477,7 +487,7 @@ constexpr int NMS4_ROWS = 4;        // rows per thread (their centre loads are i
 __global__ void __launch_bounds__(256)
 k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int H, int W, MaskSet ms, int n_masks,
                const unsigned *__restrict__ maxkey, double quality, unsigned long long *__restrict__ keys,
-               int *__restrict__ counts, int cap, const int32_t *__restrict__ enable)
+               int *__restrict__ counts, int cap, const int32_t *__restrict__ enable, int *__restrict__ hist)
 {
     const int b = blockIdx.z;
     if (enable && !enable[b]) return;
@@ -561,6 +571,7 @@ k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int 
                     if (cand) {
                         const int pos = base + __popc(bal & ((1u << lane) - 1));
                         if (pos < cap) keys[(long long)list * cap + pos] = ((unsigned long long)f2key(v[j]) << 32) | (unsigned)(y * W + x);
+                        atomicAdd(&hist[list * GF_BINS + key_bin(maxkey[list], f2key(v[j]))], 1);
                     }
                 }
             }
@@ -589,92 +600,141 @@ __global__ void __launch_bounds__(SS_NT)
 k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__ counts, int cap, int W, int H,
               int max_corners, double min_distance, int cs, int gw, int gh, unsigned *__restrict__ gnext_all,
               unsigned char *__restrict__ gstate_all, float *__restrict__ corners, int32_t *__restrict__ out_counts,
-              int max_out, const int32_t *__restrict__ enable, int n_masks)
+              int max_out, const int32_t *__restrict__ enable, int n_masks, const unsigned *__restrict__ maxkey,
+              const int *__restrict__ hist_all, unsigned long long *__restrict__ gtop_all)
 {
     extern __shared__ __align__(16) unsigned char ss_smem[];
     __shared__ int s_scan[SS_NT / 32];
-    __shared__ int s_base;
+    __shared__ int s_base, s_cut, s_ntop, s_cnt;
     const int list = blockIdx.x, tid = threadIdx.x;
     if (enable && !enable[list / n_masks]) return;
     unsigned long long *gkeys = keys_all + (long long)list * cap;
-    int n = counts[list];
-    const bool overflow = n > cap;
-    if (overflow) n = cap;
-    int npad = 32;
-    while (npad < n) npad <<= 1;
-    const bool in_smem = npad <= SS_SMEM_KEYS;
-    unsigned long long *keys = in_smem ? reinterpret_cast<unsigned long long *>(ss_smem) : gkeys;
-    unsigned *heads = reinterpret_cast<unsigned *>(ss_smem + (size_t)SS_SMEM_KEYS * 8);
-    unsigned *nxt = in_smem ? heads + SS_MAX_CELLS : gnext_all + (size_t)list * cap;
-    volatile unsigned char *state = in_smem ? reinterpret_cast<unsigned char *>(heads + SS_MAX_CELLS + SS_SMEM_KEYS)
-                                            : gstate_all + (size_t)list * cap;
-    if (in_smem)
-        for (int i = tid; i < n; i += SS_NT) keys[i] = gkeys[i];
-    for (int i = n + tid; i < npad; i += SS_NT) keys[i] = 0ull;
+    const int n_all = counts[list];
+    const bool overflow = n_all > cap;
+    const int n_full = overflow ? cap : n_all;
+    const int stop_at = (max_corners > 0 && max_corners <= max_out) ? max_corners : 0x7fffffff;
+
+    // Strongest-first prefilter: the greedy pass never looks past the candidate that completes maxCorners, so only the
+    // top `need` candidates (by histogram bin) are sorted first; the rare list that needs more is redone in full.
+    if (tid == 0) { s_cut = -1; s_ntop = n_full; }
     __syncthreads();
-    for (int k = 2; k <= npad; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (npad >> 1); t += SS_NT) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // lower index of the pair
-                int ixj = i | j;
-                unsigned long long a = keys[i], b = keys[ixj];
-                bool desc = (i & k) == 0;
-                if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+    if (hist_all && !overflow && stop_at != 0x7fffffff) {
+        const int need = stop_at + stop_at / 2 + 256;
+        if (n_full > need + need / 4) {
+            const int *hist = hist_all + list * GF_BINS;
+            const int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
+            int incl = h0 + h1;
+            const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) s_scan[wid] = incl;
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < wid; w++) woff += s_scan[w];
+            incl += woff;
+            const int excl = incl - h0 - h1;
+            if (excl < need && need <= incl) {
+                if (excl + h0 >= need) { s_cut = 2 * tid; s_ntop = excl + h0; }
+                else { s_cut = 2 * tid + 1; s_ntop = incl; }
             }
             __syncthreads();
         }
-    // low word of every key: raster index -> (y << 16 | x)
-    unsigned *xy = reinterpret_cast<unsigned *>(keys);           // xy[2*i]
-    for (int i = tid; i < n; i += SS_NT) {
-        unsigned idx = xy[2 * i];
-        unsigned y = idx / (unsigned)W, x = idx - y * (unsigned)W;
-        xy[2 * i] = (y << 16) | x;
-        state[i] = (min_distance >= 1) ? 0 : 1;
     }
-    if (min_distance >= 1) {
-        for (int i = tid; i < gw * gh; i += SS_NT) heads[i] = SS_NIL;
+    const int cut = s_cut, n_top = s_ntop;
+    const unsigned kmax = maxkey ? maxkey[list] : 0u;
+
+    int n = n_full;
+    unsigned *xy = nullptr;
+    volatile unsigned char *state = nullptr;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const bool trunc = attempt == 0 && cut >= 0 && n_top < n_full;
+        n = trunc ? n_top : n_full;
+        int npad = 32;
+        while (npad < n) npad <<= 1;
+        const bool in_smem = npad <= SS_SMEM_KEYS;
+        unsigned long long *keys = in_smem ? reinterpret_cast<unsigned long long *>(ss_smem)
+                                           : (trunc ? gtop_all + (long long)list * cap : gkeys);
+        unsigned *heads = reinterpret_cast<unsigned *>(ss_smem + (size_t)SS_SMEM_KEYS * 8);
+        unsigned *nxt = in_smem ? heads + SS_MAX_CELLS : gnext_all + (size_t)list * cap;
+        state = in_smem ? reinterpret_cast<unsigned char *>(heads + SS_MAX_CELLS + SS_SMEM_KEYS) : gstate_all + (size_t)list * cap;
         __syncthreads();
-        for (int i = tid; i < n; i += SS_NT) {
-            unsigned v = xy[2 * i];
-            int cell = ((v >> 16) / cs) * gw + (v & 0xffff) / cs;
-            nxt[i] = atomicExch(&heads[cell], (unsigned)i);
-        }
-        __syncthreads();
-        const float md2 = (float)(min_distance * min_distance);     // integer coordinates: d2 is exact
-        const bool md2_exact = (double)md2 == min_distance * min_distance;
-        // Rank-ordered windows of SS_NT candidates: every higher-ranked window is final, so only dependencies inside the
-        // window need fixed-point rounds (a few), and the scan stops as soon as maxCorners corners are accepted.
-        const int stop_at = (max_corners > 0 && max_corners <= max_out) ? max_corners : 0x7fffffff;
-        int accepted = 0;
-        for (int base = 0; base < n && accepted < stop_at; base += SS_NT) {
-            const int i = base + tid;
-            for (;;) {
-                int pending = 0;
-                if (i < n && !state[i]) {
-                    unsigned v = xy[2 * i];
-                    int x = v & 0xffff, y = v >> 16;
-                    int cx = x / cs, cy = y / cs;
-                    int verdict = 1;
-                    for (int yy = max(0, cy - 1); yy <= min(gh - 1, cy + 1) && verdict != 2; yy++)
-                        for (int xx = max(0, cx - 1); xx <= min(gw - 1, cx + 1) && verdict != 2; xx++)
-                            for (unsigned j = heads[yy * gw + xx]; j != SS_NIL; j = nxt[j]) {
-                                if ((int)j >= i) continue;
-                                unsigned u = xy[2 * j];
-                                float dx = (float)(x - (int)(u & 0xffff)), dy = (float)(y - (int)(u >> 16));
-                                float d2 = dx * dx + dy * dy;
-                                bool close = md2_exact ? (d2 < md2) : ((double)d2 < min_distance * min_distance);
-                                if (close) {
-                                    unsigned sj = state[j];
-                                    if (sj == 1) { verdict = 2; break; }
-                                    if (sj == 0) verdict = 0;
-                                }
-                            }
-                    if (verdict) state[i] = (unsigned char)verdict; else pending = 1;
-                }
-                if (!__syncthreads_or(pending)) break;
+        if (trunc) {
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            for (int i = tid; i < n_full; i += SS_NT) {
+                const unsigned long long k = gkeys[i];
+                if (key_bin(kmax, (unsigned)(k >> 32)) <= cut) keys[atomicAdd(&s_cnt, 1)] = k;
             }
-            accepted += __syncthreads_count(i < n && state[i] == 1);
+        } else if (in_smem) {
+            for (int i = tid; i < n; i += SS_NT) keys[i] = gkeys[i];
         }
+        for (int i = n + tid; i < npad; i += SS_NT) keys[i] = 0ull;
+        __syncthreads();
+        for (int k = 2; k <= npad; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (npad >> 1); t += SS_NT) {
+                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // lower index of the pair
+                    int ixj = i | j;
+                    unsigned long long a = keys[i], b = keys[ixj];
+                    bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                }
+                __syncthreads();
+            }
+        // low word of every key: raster index -> (y << 16 | x)
+        xy = reinterpret_cast<unsigned *>(keys);                     // xy[2*i]
+        for (int i = tid; i < n; i += SS_NT) {
+            unsigned idx = xy[2 * i];
+            unsigned y = idx / (unsigned)W, x = idx - y * (unsigned)W;
+            xy[2 * i] = (y << 16) | x;
+            state[i] = (min_distance >= 1) ? 0 : 1;
+        }
+        int accepted = n;
+        if (min_distance >= 1) {
+            for (int i = tid; i < gw * gh; i += SS_NT) heads[i] = SS_NIL;
+            __syncthreads();
+            for (int i = tid; i < n; i += SS_NT) {
+                unsigned v = xy[2 * i];
+                int cell = ((v >> 16) / cs) * gw + (v & 0xffff) / cs;
+                nxt[i] = atomicExch(&heads[cell], (unsigned)i);
+            }
+            __syncthreads();
+            const float md2 = (float)(min_distance * min_distance);     // integer coordinates: d2 is exact
+            const bool md2_exact = (double)md2 == min_distance * min_distance;
+            // Rank-ordered windows of SS_NT candidates: every higher-ranked window is final, so only dependencies inside
+            // the window need fixed-point rounds (a few), and the scan stops as soon as maxCorners corners are accepted.
+            accepted = 0;
+            for (int base = 0; base < n && accepted < stop_at; base += SS_NT) {
+                const int i = base + tid;
+                for (;;) {
+                    int pending = 0;
+                    if (i < n && !state[i]) {
+                        unsigned v = xy[2 * i];
+                        int x = v & 0xffff, y = v >> 16;
+                        int cx = x / cs, cy = y / cs;
+                        int verdict = 1;
+                        for (int yy = max(0, cy - 1); yy <= min(gh - 1, cy + 1) && verdict != 2; yy++)
+                            for (int xx = max(0, cx - 1); xx <= min(gw - 1, cx + 1) && verdict != 2; xx++)
+                                for (unsigned j = heads[yy * gw + xx]; j != SS_NIL; j = nxt[j]) {
+                                    if ((int)j >= i) continue;
+                                    unsigned u = xy[2 * j];
+                                    float dx = (float)(x - (int)(u & 0xffff)), dy = (float)(y - (int)(u >> 16));
+                                    float d2 = dx * dx + dy * dy;
+                                    bool close = md2_exact ? (d2 < md2) : ((double)d2 < min_distance * min_distance);
+                                    if (close) {
+                                        unsigned sj = state[j];
+                                        if (sj == 1) { verdict = 2; break; }
+                                        if (sj == 0) verdict = 0;
+                                    }
+                                }
+                        if (verdict) state[i] = (unsigned char)verdict; else pending = 1;
+                    }
+                    if (!__syncthreads_or(pending)) break;
+                }
+                accepted += __syncthreads_count(i < n && state[i] == 1);
+            }
+        }
+        if (!trunc || accepted >= stop_at) break;            // (block-uniform) otherwise: the full list, once
     }
     __syncthreads();
     // rank-ordered compaction of the accepted candidates, cut at `limit`
@@ -771,7 +831,7 @@ LKF_EXPORT int lkf_corner_min_eigen_f32(const lkf_image *src, const lkf_image *e
 }
 
 struct GfttScratch {
-    unsigned long long *keys; unsigned *maxkey; int *ccount; void *gaux;
+    unsigned long long *keys, *top; unsigned *maxkey; int *ccount, *hist; void *gaux;
     int cap, cs, gw, gh, lists;
 };
 
@@ -798,15 +858,19 @@ static int gftt_prepare(lkf_ctx *ctx, const lkf_gftt_params *p, int B, int H, in
             g->cs++;
         }
     }
-    void *keys, *cnt;
+    void *keys, *cnt, *top;
     int rc;
+    const size_t cnt_ints = (size_t)g->lists * (2 + GF_BINS);
     if ((rc = lkf_scratch(ctx, 0, (size_t)g->lists * g->cap * 8, &keys)) != LKF_OK) return rc;
-    if ((rc = lkf_scratch(ctx, 1, (size_t)g->lists * 2 * sizeof(int), &cnt)) != LKF_OK) return rc;
+    if ((rc = lkf_scratch(ctx, 1, cnt_ints * sizeof(int), &cnt)) != LKF_OK) return rc;
     if ((rc = lkf_scratch(ctx, 2, (size_t)g->lists * g->cap * 5, &g->gaux)) != LKF_OK) return rc;     // next (u32) + state (u8), large lists only
+    if ((rc = lkf_scratch(ctx, 4, (size_t)g->lists * g->cap * 8, &top)) != LKF_OK) return rc;        // strongest candidates of large lists
     g->keys = (unsigned long long *)keys;
+    g->top = (unsigned long long *)top;
     g->maxkey = (unsigned *)cnt;
     g->ccount = (int *)cnt + g->lists;
-    LKF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)g->lists * 2 * sizeof(int), (cudaStream_t)stream));
+    g->hist = (int *)cnt + 2 * g->lists;
+    LKF_CUDA(cudaMemsetAsync(cnt, 0, cnt_ints * sizeof(int), (cudaStream_t)stream));
     return LKF_OK;
 }
 
@@ -825,11 +889,11 @@ static int gftt_passes(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *
     if (aligned_to(eig, 16)) {
         dim3 g4((W + 127) / 128, (H - 2 + 8 * NMS4_ROWS - 1) / (8 * NMS4_ROWS), B);
         k_nms_compact4<<<g4, 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, g.maxkey,
-                                          p->quality_level, g.keys, g.ccount, g.cap, enable);
+                                          p->quality_level, g.keys, g.ccount, g.cap, enable, g.hist);
     } else {
         dim3 g2((W - 2 + 31) / 32, (H - 2 + 7) / 8, B);
         k_nms_compact<<<g2, 256, 0, s>>>((const float *)eig->data, eig->row_pitch, eig->image_pitch, H, W, ms, n_masks, g.maxkey,
-                                         p->quality_level, g.keys, g.ccount, g.cap, enable);
+                                         p->quality_level, g.keys, g.ccount, g.cap, enable, g.hist);
     }
     LKF_LAUNCH_CHECK(ctx);
     const size_t ss_smem = (size_t)SS_SMEM_KEYS * 8 + (size_t)SS_MAX_CELLS * 4 + (size_t)SS_SMEM_KEYS * 4 + SS_SMEM_KEYS;
@@ -840,7 +904,7 @@ static int gftt_passes(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *
     }
     k_sort_select<<<g.lists, SS_NT, ss_smem, s>>>(g.keys, g.ccount, g.cap, W, H, p->max_corners, p->min_distance, g.cs, g.gw,
                                                  g.gh, (unsigned *)g.gaux, (unsigned char *)g.gaux + (size_t)g.lists * g.cap * 4, corners,
-                                                 counts, max_out, enable, n_masks);
+                                                 counts, max_out, enable, n_masks, g.maxkey, g.hist, g.top);
     LKF_LAUNCH_CHECK(ctx);
     return LKF_OK;
 }
