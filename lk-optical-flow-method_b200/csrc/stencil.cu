@@ -344,11 +344,15 @@ bool stream_ok(const lkf_image *src, const lkf_image *dst)
 
 // ---------------------------------------------------------------------------------------------
 // a3 streaming form (source rows 16-byte aligned, W_src % 16 == 0): a thread owns 8 output columns
-// (16 source columns + 2 left + 1 right neighbour), slides down; the horizontal [1 4 6 4 1] sums of a
-// source row are packed two per register (<= 4080), five rows of them live in registers, and the
-// vertical pass + rounding run on the packed pairs (16*4080 + 128 < 2^16, no carry between halves).
+// (16 source columns + 2 left + 1 right neighbour) and slides down, two output rows per iteration.
+// Horizontal [1 4 6 4 1] at the even centres by DP4A on the raw bytes: the four bytes c-2..c+1 are a
+// source word (odd outputs) or two words funnel-shifted by 16 bits (even outputs), dotted with the
+// packed weights (1,4,6,4); the fifth tap s[c+2] is a second DP4A with a one-hot weight word.  The
+// sums (<= 4080) are packed two per register, five rows of them live in registers, and the vertical
+// pass + rounding run on the packed pairs (16*4080 + 128 < 2^16, no carry between the halves).
 // ---------------------------------------------------------------------------------------------
-// raw bytes of one source row for a thread: 16 columns + the word left of them + the byte right of them
+// raw bytes of one source row for a thread: 16 columns, the word left of them (its bytes 2, 3 = columns -2, -1) and the
+// byte right of them; REFLECT_101 at the left / right image border is resolved here
 struct PdRaw { uint4 v; uint32_t l, r; };
 __device__ __forceinline__ PdRaw pd_load_row(const uint8_t *__restrict__ S, long long srp, int y, int Hs, int xs, int Ws)
 {
@@ -356,34 +360,42 @@ __device__ __forceinline__ PdRaw pd_load_row(const uint8_t *__restrict__ S, long
     const uint8_t *row = S + (long long)y * srp;
     PdRaw q;
     q.v = __ldg(reinterpret_cast<const uint4 *>(row + xs));
-    q.l = xs > 0 ? __ldg(reinterpret_cast<const uint32_t *>(row + xs - 4)) : 0u;
-    q.r = xs + 16 < Ws ? (uint32_t)__ldg(row + xs + 16) : 0u;
+    q.l = xs > 0 ? __ldg(reinterpret_cast<const uint32_t *>(row + xs - 4)) : __byte_perm(q.v.x, 0u, 0x1200);   // columns -2, -1 -> 2, 1
+    q.r = xs + 16 < Ws ? (uint32_t)__ldg(row + xs + 16) : (q.v.w >> 16) & 255u;                               // column Ws -> Ws-2
     return q;
 }
 
-__device__ __forceinline__ void pd_hsum_row(const PdRaw &q, int xs, int Ws, uint32_t (&h)[4])
+// same, for a row known to be inside the image: p = address of column xs of the row (warp-uniform fast path of the loop)
+__device__ __forceinline__ PdRaw pd_load_row_at(const uint8_t *__restrict__ p, bool has_left, bool has_right)
 {
-    // Packed form: E(w) = even columns of a word as two 16-bit lanes, O(w) = odd columns.  Output pair k (centres 4k, 4k+2):
-    //   (s[c-2] + s[c+2]) + 4 (s[c-1] + s[c+1]) + 6 s[c]  =  L2 + R2 + 4 (L1 + R1) + 6 C   with
-    //   C = E(w[k]), R1 = O(w[k]), L2 = (E(w[k-1]).hi, E(w[k]).lo), R2 = (E(w[k]).hi, E(w[k+1]).lo), L1 = (O(w[k-1]).hi, O(w[k]).lo).
-    const uint32_t w[4] = {q.v.x, q.v.y, q.v.z, q.v.w};
-    uint32_t E[6], O[5];                       // E[k+1] = E(w[k]); E[0] / O[0]: left neighbour word, E[5]: right neighbour
-#pragma unroll
-    for (int k = 0; k < 4; k++) { E[k + 1] = w[k] & 0x00ff00ffu; O[k + 1] = (w[k] >> 8) & 0x00ff00ffu; }
-    if (xs > 0) { E[0] = q.l & 0x00ff00ffu; O[0] = (q.l >> 8) & 0x00ff00ffu; }
-    else { E[0] = E[1]; O[0] = O[1] << 16; }                                // columns -2, -1 -> 2, 1
-    E[5] = xs + 16 < Ws ? q.r : E[4] >> 16;                                  // column Ws -> Ws-2
+    PdRaw q;
+    q.v = __ldg(reinterpret_cast<const uint4 *>(p));
+    q.l = 0u; q.r = 0u;
+    if (has_left) q.l = __ldg(reinterpret_cast<const uint32_t *>(p - 4));
+    if (has_right) q.r = (uint32_t)__ldg(p + 16);
+    if (!has_left) q.l = __byte_perm(q.v.x, 0u, 0x1200);
+    if (!has_right) q.r = (q.v.w >> 16) & 255u;
+    return q;
+}
+
+__device__ __forceinline__ void pd_hsum_row(const PdRaw &q, uint32_t (&h)[4])
+{
+    const uint32_t w[5] = {q.v.x, q.v.y, q.v.z, q.v.w, q.r};
+    uint32_t left = q.l;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const uint32_t L2 = __byte_perm(E[k], E[k + 1], 0x5432), R2 = __byte_perm(E[k + 1], E[k + 2], 0x5432);
-        const uint32_t L1 = __byte_perm(O[k], O[k + 1], 0x5432);
-        h[k] = L2 + R2 + 4u * (L1 + O[k + 1]) + 6u * E[k + 1];
+        // outputs 2k (centre = byte 0 of w[k]) and 2k+1 (centre = byte 2 of w[k])
+        const uint32_t f = __funnelshift_r(left, w[k], 16);                       // bytes c-2 .. c+1 of the even output
+        const uint32_t e = __dp4a(f, 0x04060401u, __dp4a(w[k], 0x00010000u, 0u));
+        const uint32_t o = __dp4a(w[k], 0x04060401u, __dp4a(w[k + 1], 0x00000001u, 0u));
+        h[k] = o * 65536u + e;
+        left = w[k];
     }
 }
 
-__global__ void __launch_bounds__(SV_NT) k_pyrdown_stream(const uint8_t *__restrict__ src, long long srp, long long sip,
-                                                          uint8_t *__restrict__ dst, long long drp, long long dip, int Hs, int Ws,
-                                                          int Hd, int Wd, int rows_per_block)
+__global__ void __launch_bounds__(SV_NT, 8) k_pyrdown_stream(const uint8_t *__restrict__ src, long long srp, long long sip,
+                                                             uint8_t *__restrict__ dst, long long drp, long long dip, int Hs, int Ws,
+                                                             int Hd, int Wd, int rows_per_block)
 {
     const int xo = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (xo >= Wd) return;
@@ -391,26 +403,44 @@ __global__ void __launch_bounds__(SV_NT) k_pyrdown_stream(const uint8_t *__restr
     const uint8_t *S = src + (long long)b * sip;
     uint8_t *D = dst + (long long)b * dip + xo;
     const int y0 = blockIdx.y * rows_per_block, y1 = min(Hd, y0 + rows_per_block);
-    uint32_t r0[4], r1[4], r2[4], r3[4], r4[4];
+    const bool has_left = xs > 0, has_right = xs + 16 < Ws;
+    uint32_t r0[4], r1[4], r2[4], r3[4], r4[4], r5[4], r6[4];
     {
         const PdRaw q0 = pd_load_row(S, srp, 2 * y0 - 2, Hs, xs, Ws), q1 = pd_load_row(S, srp, 2 * y0 - 1, Hs, xs, Ws),
                     q2 = pd_load_row(S, srp, 2 * y0, Hs, xs, Ws);
-        pd_hsum_row(q0, xs, Ws, r0); pd_hsum_row(q1, xs, Ws, r1); pd_hsum_row(q2, xs, Ws, r2);
+        pd_hsum_row(q0, r0); pd_hsum_row(q1, r1); pd_hsum_row(q2, r2);
     }
-    // the two source rows of the next output row are loaded one iteration ahead (more bytes in flight per thread)
-    PdRaw na = pd_load_row(S, srp, 2 * y0 + 1, Hs, xs, Ws), nb = pd_load_row(S, srp, 2 * y0 + 2, Hs, xs, Ws);
-    for (int y = y0; y < y1; y++) {
-        const PdRaw qa = na, qb = nb;
-        if (y + 1 < y1) { na = pd_load_row(S, srp, 2 * y + 3, Hs, xs, Ws); nb = pd_load_row(S, srp, 2 * y + 4, Hs, xs, Ws); }
-        pd_hsum_row(qa, xs, Ws, r3);
-        pd_hsum_row(qb, xs, Ws, r4);
+    auto vstore = [&](uint8_t *drow, const uint32_t (&a)[4], const uint32_t (&bb)[4], const uint32_t (&c)[4], const uint32_t (&d)[4],
+                      const uint32_t (&e)[4]) {
         uint32_t o[4];
 #pragma unroll
         for (int k = 0; k < 4; k++)
-            o[k] = ((r0[k] + r4[k] + 0x00800080u + 4u * (r1[k] + r3[k]) + 6u * r2[k]) >> 8) & 0x00ff00ffu;
-        *reinterpret_cast<uint2 *>(D + (long long)y * drp) = make_uint2(__byte_perm(o[0], o[1], 0x6420), __byte_perm(o[2], o[3], 0x6420));
+            o[k] = ((a[k] + e[k] + 0x00800080u + 4u * (bb[k] + d[k]) + 6u * c[k]) >> 8) & 0x00ff00ffu;
+        *reinterpret_cast<uint2 *>(drow) = make_uint2(__byte_perm(o[0], o[1], 0x6420), __byte_perm(o[2], o[3], 0x6420));
+    };
+    // Two output rows per iteration; the two source rows of an output row are loaded while the previous output row is
+    // computed.  Rows 2y+1 .. 2y+6 of an iteration are inside the image except in the last block(s) of an image
+    // (warp-uniform): pointer bumps on the fast path, mirrored row indices otherwise (an overshoot of up to 4 rows past
+    // the rows actually used still mirrors into the image: Hs >= 4).
+    const uint8_t *p = S + (long long)(2 * y0 + 1) * srp + xs;            // row 2y+1 of the current iteration
+    uint8_t *drow = D + (long long)y0 * drp;
+    PdRaw qa = pd_load_row(S, srp, 2 * y0 + 1, Hs, xs, Ws), qb = pd_load_row(S, srp, 2 * y0 + 2, Hs, xs, Ws);
+    for (int y = y0; y < y1; y += 2) {
+        const bool fast = 2 * y + 6 < Hs;
+        PdRaw qc, qd;
+        if (fast) { qc = pd_load_row_at(p + 2 * srp, has_left, has_right); qd = pd_load_row_at(p + 3 * srp, has_left, has_right); }
+        else { qc = pd_load_row(S, srp, 2 * y + 3, Hs, xs, Ws); qd = pd_load_row(S, srp, 2 * y + 4, Hs, xs, Ws); }
+        pd_hsum_row(qa, r3); pd_hsum_row(qb, r4);
+        vstore(drow, r0, r1, r2, r3, r4);
+        if (fast) { qa = pd_load_row_at(p + 4 * srp, has_left, has_right); qb = pd_load_row_at(p + 5 * srp, has_left, has_right); }
+        else { qa = pd_load_row(S, srp, 2 * y + 5, Hs, xs, Ws); qb = pd_load_row(S, srp, 2 * y + 6, Hs, xs, Ws); }
+        if (y + 1 < y1) {
+            pd_hsum_row(qc, r5); pd_hsum_row(qd, r6);
+            vstore(drow + drp, r2, r3, r4, r5, r6);
+        }
 #pragma unroll
-        for (int k = 0; k < 4; k++) { r0[k] = r2[k]; r1[k] = r3[k]; r2[k] = r4[k]; }
+        for (int k = 0; k < 4; k++) { r0[k] = r4[k]; r1[k] = r5[k]; r2[k] = r6[k]; }
+        p += 4 * srp; drow += 2 * drp;
     }
 }
 

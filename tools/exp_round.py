@@ -1,0 +1,52 @@
+"""Tuning experiment (one process per setting: the switches are read once): LK stage and pyramid stage timings of the
+bench workload under LKF_LK_VARIANT / LKF_LK_PERSIST / LKF_PD_ROWS, with a checksum of the outputs.
+Usage: exp_round.py lk|pyr [B]"""
+import hashlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from lk_optical_flow_method_b200 import ops, synth
+
+what = sys.argv[1]
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+H, W = 1080, 1920
+tex = torch.from_numpy(synth.make_texture(W, H, 0)).cuda()
+frames = torch.stack([synth.zoom_frame(tex, W, H, t) for t in range(B + 1)])
+gray = ops.process_img(frames)
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+def digest(*ts):
+    h = hashlib.sha1()
+    for t in ts:
+        h.update(t.detach().cpu().numpy().tobytes())
+    return h.hexdigest()[:12]
+
+
+tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("LKF_"))
+if what == "lk":
+    from lk_optical_flow_method_b200.pipeline import PairPipeline
+    LK = dict(winSize=(21, 21), maxLevel=2, criteria=(3, 10, 0.03))
+    pipe = PairPipeline(B, H, W, 2000, LK, None, 0)
+    pipe.prime(frames[0])
+    pipe.stage_process(frames[1:]); pipe.stage_pyramid()
+    e = ops.min_eigen(gray[:B], 7)
+    cor, cnt = ops.gftt_select(e, None, 2000, 0.01, 7, 2000)
+    pipe.set_points(cor, cnt)
+    us = timeit(pipe.stage_track)
+    outs = [getattr(pipe, n) for n in ("next_pts", "status", "err") if hasattr(pipe, n)]
+    print(f"[{tag}] lk stage {us:8.1f} us per {B} pairs  digest {digest(*outs) if outs else '-'}")
+else:
+    l1 = ops.pyr_down(gray); l2 = ops.pyr_down(l1)
+    a = timeit(lambda: ops.pyr_down(gray, out=l1)); b = timeit(lambda: ops.pyr_down(l1, out=l2))
+    print(f"[{tag}] pyrdown L0->L1 {a:7.1f} us  L1->L2 {b:7.1f} us per {B + 1} frames  digest {digest(l1, l2)}")
