@@ -500,9 +500,12 @@ LKF_EXPORT int lkf_pyr_down_u8(const lkf_image *src, const lkf_image *dst, lkf_s
         dst->height != (src->height + 1) / 2 || dst->width != (src->width + 1) / 2)
         return LKF_ERR_ARG;
     if (src->width % 16 == 0 && src->width >= 32 && src->height >= 4 && aligned_to(src, 16) && aligned_to(dst, 8)) {
-        const int R = 16;
+        // rows per CTA: 16, fewer when that leaves the GPU short of about one wave of resident warps (small levels)
         const int nt = stream_threads(dst->width / 8);
-        dim3 g((dst->width / 8 + nt - 1) / nt, (dst->height + R - 1) / R, dst->batch);
+        const int gx = (dst->width / 8 + nt - 1) / nt;
+        int R = 16;
+        while (R > 4 && (long long)gx * ((dst->height + R - 1) / R) * dst->batch * (nt / 32) < 148LL * 28) R >>= 1;
+        dim3 g(gx, (dst->height + R - 1) / R, dst->batch);
         k_pyrdown_stream<<<g, nt, 0, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch,
                                                                 (uint8_t *)dst->data, dst->row_pitch, dst->image_pitch, src->height,
                                                                 src->width, dst->height, dst->width, R);
