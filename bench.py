@@ -40,8 +40,8 @@ WORKLOAD = ("C2: 1920x1080 sparse PyrLK, 2000 pts/pair, 3-level pyramid (maxLeve
             "refresh on every 10th pair")
 METRIC = "frame-pairs/s, 1080p PyrLK 2k pts"
 # dram__bytes_read.sum + dram__bytes_write.sum per frame pair, from the committed ncu --set full captures
-NCU_SOURCE = "profiles/r01_captureD_kernels.md (ncu --set full, per step of 64 pairs, divided by 64)"
-NCU_DRAM_BYTES_PER_PAIR = {"lk_track": (162.7e6 + 5.4e6 + 35.4e6 + 1.6e6) / 64, "process_img": (422.5e6 + 113.7e6) / 64}
+NCU_SOURCE = "profiles/r01_captureE_kernels.md (ncu --set full, per step of 64 pairs, divided by 64)"
+NCU_DRAM_BYTES_PER_PAIR = {"lk_track": (162.3e6 + 7.4e6 + 35.4e6 + 0.4e6) / 64, "process_img": (422.5e6 + 113.4e6) / 64}
 
 
 def env_int(name, default):
