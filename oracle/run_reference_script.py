@@ -69,9 +69,35 @@ def _install_shims():
     cv2.destroyAllWindows = lambda *a, **k: None
 
 
-def run(script, video_name, workdir, overrides=None, quiet=True):
+VL_FIELDS = ("m", "intercept", "mv", "interceptv", "bp_x", "bp_y", "lp_y", "rp_y", "up_x", "dp_x")
+
+
+class VLRecorder:
+    """Records the state of the script's `vl` object (class VL, VP.py:196-250; a local of Run()) after every
+    `vl.update(...)` call (VP.py:654: once per frame while the VP is initialised) WITHOUT touching the script: a
+    sys.setprofile hook looks at the return event of VL.update.  One row per call: VL_FIELDS, NaN while the object is
+    not initialised (no VP movement yet)."""
+
+    def __init__(self, script):
+        self.script = os.path.abspath(script)
+        self.rows = []
+
+    def __call__(self, frame, event, arg):
+        if event != "return" or frame.f_code.co_name != "update":
+            return
+        vl = frame.f_locals.get("self")
+        if vl is None or type(vl).__name__ != "VL" or os.path.abspath(frame.f_code.co_filename) != self.script:
+            return
+        if not vl._isinit:
+            self.rows.append([float("nan")] * len(VL_FIELDS))
+        else:
+            self.rows.append([float(vl._m), float(vl._intercept), float(vl._mv), float(vl._interceptv), float(vl._bp[0]),
+                              float(vl._bp[1]), float(vl._lp[1]), float(vl._rp[1]), float(vl._up[0]), float(vl._dp[0])])
+
+
+def run(script, video_name, workdir, overrides=None, quiet=True, want_vl=False):
     """Execute `script` (path under /root/reference) on `video_name` (a file or %04d pattern inside
-    workdir).  Returns the text of ./vps/vps_<name>.csv."""
+    workdir).  Returns the text of ./vps/vps_<name>.csv (and, if want_vl, the VLRecorder rows of the run)."""
     _install_shims()
     os.makedirs(os.path.join(workdir, "vps"), exist_ok=True)
     os.makedirs(os.path.join(workdir, "saved_video"), exist_ok=True)
@@ -79,7 +105,10 @@ def run(script, video_name, workdir, overrides=None, quiet=True):
     os.chdir(workdir)
     sys.argv = [script, video_name]
     out = sys.stdout
+    rec = VLRecorder(script) if want_vl else None
     try:
+        if rec is not None:
+            sys.setprofile(rec)
         if quiet:
             sys.stdout = open(os.devnull, "w")
         if overrides:
@@ -92,9 +121,11 @@ def run(script, video_name, workdir, overrides=None, quiet=True):
         else:
             runpy.run_path(script, run_name="__main__")
     finally:
+        sys.setprofile(None)
         sys.stdout = out
         os.chdir(cwd)
         sys.argv = argv
     name = video_name.split("\\")[-1].split(".")[0]
     with open(os.path.join(workdir, "vps", f"vps_{name}.csv"), newline="") as f:
-        return f.read()
+        text = f.read()
+    return (text, rec.rows) if want_vl else text

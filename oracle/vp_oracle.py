@@ -10,10 +10,12 @@ behavioural notes in SURVEY.md Appendix B.6, following -- including their quirks
   VP init / update / hide, CSV rows        VP_detection_using_optical_flow.py:157-194, 596-653   (B.2-B.4)
   corner refresh                           VP_detection_using_optical_flow.py:700-718
   save_csv                                 VP_detection_using_optical_flow.py:388-392
+  vanishing-line pair (class VL)           VP_detection_using_optical_flow.py:196-250, 654       (drawing only)
 
 `variant="LKF"` applies the LK_Final.py differences.  PINNING: oracle/make_golden.py runs
-the UNMODIFIED scripts on synthetic clips and stores their CSVs in tests/golden/; with cv2 as the `cvm`
-argument run_clip() reproduces those CSVs byte for byte (tests/test_vp_oracle_golden.py).
+the UNMODIFIED scripts on synthetic clips and stores their CSVs (and the state of their `vl` object after every
+update call, vl_*.npz) in tests/golden/; with cv2 as the `cvm` argument run_clip() reproduces those CSVs byte for
+byte and the vanishing-line states to 1e-9 (tests/test_vp_oracle_golden.py).
 
 No class or function of the reference is reused: state is a dict, lines and points are tuples.
 """
@@ -26,7 +28,7 @@ import numpy as np
 
 DEFAULTS = dict(WID=860, TP_NUM=20, VP_REF_NUM=10, VP_UPDATE_RATE=0.5, FL_UPDATE_RATE=0.05, TP_UPDATE_RATE=0.3,
                 TP_UPDATE_TIME=10, MIN_ANG_DIF=25, MAX_CP_STD=1.0, MIN_FL_LEN=1.0, CP_THOLD=1 / 15, HIDE_VP_THOLD=50,
-                START_X_FILTER=True, RESET_AVG_ON_HIDE=True)
+                START_X_FILTER=True, RESET_AVG_ON_HIDE=True, VP_REF=300)
 LKF_OVERRIDES = dict(VP_REF_NUM=15, MIN_FL_LEN=1.5, START_X_FILTER=False, RESET_AVG_ON_HIDE=False)
 
 
@@ -133,7 +135,50 @@ def intersect(l1, l2):
 
 def new_state(p):
     return dict(vp=None, recent=[], avg=[p["MIN_FL_LEN"], p["MIN_FL_LEN"]], vp_ult=0, tp_ult=0, rows=[], n_lines=0,
-                n_cps=0)
+                n_cps=0, moved=False, vl=None, vl_rows=[])
+
+
+# ---------------------------------------------------------------------------------------------------
+# vanishing-line pair (VP.py:196-250): least-squares lines y(x) and x(y) through the last VP_REF history rows,
+# re-anchored at the current VP.  scipy.stats.linregress (1.18) computes slope = (dx.dy / n) / (dx.dx / n) on the
+# de-meaned samples and intercept = ymean - slope * xmean; restated with numpy only.
+# ---------------------------------------------------------------------------------------------------
+VL_FIELDS = ("m", "intercept", "mv", "interceptv", "bp_x", "bp_y", "lp_y", "rp_y", "up_x", "dp_x")
+
+
+def linfit(x, y):
+    x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+    n = len(x)
+    xm, ym = np.mean(x), np.mean(y)
+    dx, dy = x - xm, y - ym
+    with np.errstate(all="ignore"):
+        slope = (np.dot(dx, dy) / n) / (np.dot(dx, dx) / n)
+    return slope, ym - slope * xm
+
+
+def vl_update(S, p, Hei):
+    """VL.update(all_vp[-VP_REF:], vp) (VP.py:224-245, called at VP.py:654): nothing until the VP has moved once."""
+    if S["moved"]:
+        WID = p["WID"]
+        hist = S["rows"][-p["VP_REF"]:]
+        x, y = [r[0] for r in hist], [r[1] for r in hist]
+        m, b = linfit(x, y)
+        mv, bv = linfit(y, x)
+        bx, by = S["vp"][0], S["vp"][1]
+        S["vl"] = dict(m=m, intercept=b, mv=mv, interceptv=bv, bp_x=bx, bp_y=by, lp_y=by - bx * m,
+                       rp_y=by + (WID - 1 - bx) * m, up_x=bx - by * mv, dp_x=bx + (Hei - 1 - by) * mv)
+    S["vl_rows"].append([float("nan")] * len(VL_FIELDS) if S["vl"] is None else [S["vl"][k] for k in VL_FIELDS])
+
+
+def vl_endpoints(vl, WID, Hei, mode="best_point"):
+    """VL.__call__ (VP.py:213-221, 245-250): (left, right, up, down, st); st is always True once initialised (the
+    script's `is not nan` compares object identity)."""
+    if vl is None:
+        return None, None, None, None, None
+    if mode == "best_point":
+        return (0, vl["lp_y"]), (WID - 1, vl["rp_y"]), (vl["up_x"], 0), (vl["dp_x"], Hei - 1), True
+    return ((0, vl["intercept"]), (WID - 1, vl["intercept"] + (WID - 1) * vl["m"]), (vl["interceptv"], 0),
+            (vl["interceptv"] + (Hei - 1) * vl["mv"], Hei - 1), True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -189,6 +234,7 @@ def vp_frame(S, tracks, p, Hei):
                 acc = acc / cnt
                 vp[0] = vp[0] + acc[0] * p["VP_UPDATE_RATE"]
                 vp[1] = vp[1] + acc[1] * p["VP_UPDATE_RATE"]
+                S["moved"] = True                     # Point.update sets _moved (VP.py:180)
                 S["rows"].append((vp[0], vp[1]))
                 S["vp_ult"] = 0
         elif len(S["recent"]) >= p["VP_REF_NUM"]:
@@ -198,15 +244,18 @@ def vp_frame(S, tracks, p, Hei):
             acc = acc / p["VP_REF_NUM"]
             cp[0], cp[1] = acc[0], acc[1]             # the last CP object BECOMES the VP (aliasing kept)
             S["vp"] = cp
+            S["moved"] = False                        # ... a cross-point object that has never been update()d
             S["vp_ult"] = 0
     if S["vp"] is not None:
         if S["vp_ult"] > p["HIDE_VP_THOLD"]:
             S["vp"] = None
+            S["moved"] = False                        # a fresh Point(isVP=True); the VL object keeps its last lines
             S["recent"] = []
             if p["RESET_AVG_ON_HIDE"]:
                 S["avg"] = [p["MIN_FL_LEN"], p["MIN_FL_LEN"]]
         else:
             S["rows"].append((S["vp"][0], S["vp"][1]))
+            vl_update(S, p, Hei)
     return S
 
 
