@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LKF_ABI_VERSION 1
+#define LKF_ABI_VERSION 2
 #define LKF_MAX_LEVELS 8
 
 typedef enum lkf_status {
@@ -75,6 +75,9 @@ typedef struct lkf_gftt_params {
 
 /* ---- library / workspace ------------------------------------------------------------------ */
 int lkf_abi_version(void);
+/* sizeof of an ABI struct as compiled into the library (host arithmetic; bindings check their mirror against it):
+ * 0 lkf_image, 1 lkf_lk_params, 2 lkf_gftt_params, 3 lkf_vp_params, 4 lkf_vp_state; -1 otherwise */
+int lkf_struct_size(int which);
 const char *lkf_strerror(int status);
 const char *lkf_last_error(void);                 /* text of the last CUDA failure on this thread */
 int lkf_ctx_create(int device, lkf_ctx **out);
@@ -154,7 +157,7 @@ typedef struct lkf_vp_params {
     int32_t hide_vp_thold;             /* HIDE_VP_THOLD = 50                    (VP.py:644)          */
     int32_t reset_avg_on_hide;         /* 1: VP.py:647, 0: LK_Final.py                               */
     int32_t tp_update_time;            /* TP_UPDATE_TIME = 10                   (VP.py:700)          */
-    int32_t reserved;
+    int32_t vl_ref;                    /* VP_REF = 300: history rows of the vanishing-line fits (VP.py:52, 654); 0 = no VL */
 } lkf_vp_params;
 
 typedef struct lkf_vp_state {          /* one per clip, device resident, zero-initialised except avg_len */
@@ -164,13 +167,20 @@ typedef struct lkf_vp_state {          /* one per clip, device resident, zero-in
     int32_t ring_alias[LKF_VP_RING];   /* 1: this entry IS the VP object (init aliasing) */
     int32_t vp_init, ring_count, ring_head, vp_ult, tp_ult, n_rows, row_overflow, refresh;
     int64_t n_lines, n_cps;
+    /* vanishing-line pair, class VL (VP.py:196-250): least-squares lines y = m x + b and x = mv y + bv through the last
+     * vl_ref rows, re-anchored at the VP; updated once per frame while the VP is shown and has moved (VP.py:654, 226) */
+    int32_t vp_moved;                  /* Point._moved of the current VP object (VP.py:180); cleared by init / hide */
+    int32_t vl_init;                   /* VL._isinit: the fields below are valid                              */
+    double vl_m, vl_b, vl_mv, vl_bv;   /* slope, intercept of y(x); slope, intercept of x(y)                  */
+    double vl_bp[2];                   /* VP at the last update                                               */
+    double vl_lp_y, vl_rp_y, vl_up_x, vl_dp_x;   /* end points (0, lp_y), (WID-1, rp_y), (up_x, 0), (dp_x, Hei-1) */
 } lkf_vp_state;
 
 /* p0/p1: [n_clips*2][max_pts_per_group][2] float32 (group g of clip b at list 2b+g), status likewise u8,
  * counts [n_clips*2] int32 (in: tracked points per group; out: survivors, which p0 now holds = `p0s[n] = good_new`).
  * rows: [n_clips][row_capacity][2] float64, appended at states[b].n_rows.  clip_enable (nullable): skip clip b if 0. */
 int lkf_vp_frame(const lkf_vp_params *params, lkf_vp_state *states, int n_clips, float *p0, const float *p1,
-                 const uint8_t *status, int32_t *counts, int max_pts_per_group, const lkf_image *roi_mask,
+                 const uint8_t *status, int32_t *counts, int max_pts_per_group, const lkf_image *roi_mask /* gives WID, Hei */,
                  double *rows, int row_capacity, int32_t *refresh_out /* nullable: [n_clips] copy of state.refresh */,
                  const int32_t *clip_enable, lkf_stream stream);
 /* REPlace refresh (VP.py:700-718) from a 4-mask corner detection: lists 4b+0,1 -> group 0, 4b+2,3 -> group 1,

@@ -8,6 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "csrc", "liblkflow_b200.so")
+ABI_VERSION = 2          # LKF_ABI_VERSION of include/lkflow_b200.h
 
 LKF_MAX_LEVELS = 8
 
@@ -48,7 +49,7 @@ class LkfVpParams(ctypes.Structure):
                 ("tp_refresh_below", ctypes.c_double), ("start_x_sep", ctypes.c_float),
                 ("vp_ref_num", ctypes.c_int32), ("hide_vp_thold", ctypes.c_int32),
                 ("reset_avg_on_hide", ctypes.c_int32), ("tp_update_time", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("vl_ref", ctypes.c_int32)]
 
 
 class LkfVpState(ctypes.Structure):
@@ -58,7 +59,11 @@ class LkfVpState(ctypes.Structure):
                 ("vp_init", ctypes.c_int32), ("ring_count", ctypes.c_int32), ("ring_head", ctypes.c_int32),
                 ("vp_ult", ctypes.c_int32), ("tp_ult", ctypes.c_int32), ("n_rows", ctypes.c_int32),
                 ("row_overflow", ctypes.c_int32), ("refresh", ctypes.c_int32),
-                ("n_lines", ctypes.c_int64), ("n_cps", ctypes.c_int64)]
+                ("n_lines", ctypes.c_int64), ("n_cps", ctypes.c_int64),
+                ("vp_moved", ctypes.c_int32), ("vl_init", ctypes.c_int32),
+                ("vl_m", ctypes.c_double), ("vl_b", ctypes.c_double), ("vl_mv", ctypes.c_double), ("vl_bv", ctypes.c_double),
+                ("vl_bp", ctypes.c_double * 2), ("vl_lp_y", ctypes.c_double), ("vl_rp_y", ctypes.c_double),
+                ("vl_up_x", ctypes.c_double), ("vl_dp_x", ctypes.c_double)]
 
 
 _P = ctypes.POINTER
@@ -68,6 +73,7 @@ _i = ctypes.c_int
 # name -> (restype, argtypes); every symbol include/lkflow_b200.h declares must be listed here
 SIGNATURES = {
     "lkf_abi_version": (_i, []),
+    "lkf_struct_size": (_i, [_i]),
     "lkf_strerror": (ctypes.c_char_p, [_i]),
     "lkf_last_error": (ctypes.c_char_p, []),
     "lkf_ctx_create": (_i, [_i, _P(_vp)]),
@@ -108,8 +114,12 @@ def load():
         fn = getattr(lib, name)      # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.lkf_abi_version() != 1:
+    if lib.lkf_abi_version() != ABI_VERSION:
         raise ImportError("liblkflow_b200.so ABI version mismatch; rebuild")
+    for which, cls in enumerate((LkfImage, LkfLkParams, LkfGfttParams, LkfVpParams, LkfVpState)):
+        if lib.lkf_struct_size(which) != ctypes.sizeof(cls):
+            raise ImportError(f"{cls.__name__}: ctypes mirror is {ctypes.sizeof(cls)} bytes, the library's struct "
+                              f"{lib.lkf_struct_size(which)}; rebuild")
     _lib = lib
     return lib
 

@@ -37,6 +37,18 @@ int lkf_scratch(lkf_ctx *ctx, int slot, size_t bytes, void **out)
 
 LKF_EXPORT int lkf_abi_version(void) { return LKF_ABI_VERSION; }
 
+LKF_EXPORT int lkf_struct_size(int which)
+{
+    switch (which) {
+        case 0: return (int)sizeof(lkf_image);
+        case 1: return (int)sizeof(lkf_lk_params);
+        case 2: return (int)sizeof(lkf_gftt_params);
+        case 3: return (int)sizeof(lkf_vp_params);
+        case 4: return (int)sizeof(lkf_vp_state);
+        default: return -1;
+    }
+}
+
 LKF_EXPORT const char *lkf_strerror(int status)
 {
     switch (status) {

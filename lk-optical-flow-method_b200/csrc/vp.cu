@@ -7,7 +7,9 @@
 //                                                                      VP.py:296-324, 581-595   
 //   a12 VP gate / init (aliasing quirk) / +-1 sigma inlier update / hide, CSV rows
 //                                                                      VP.py:157-194, 596-653   
-//   plus the refresh decision of VP.py:700 and the REPlace of VP.py:713-715 (k_apply_refresh).
+//   plus the refresh decision of VP.py:700 and the REPlace of VP.py:713-715 (k_apply_refresh), and the vanishing-line
+//   pair of class VL (VP.py:196-250, updated at VP.py:654; drawing only in the scripts): two least-squares fits over the
+//   last VP_REF history rows, summed by the whole CTA.
 //
 // Pair geometry is evaluated by the whole CTA (ballot + prefix compaction keeps combinations order); the
 // vanishing-point recurrence itself is strictly sequential (the gate uses the current VP) and runs on
@@ -72,6 +74,7 @@ __device__ void consume_cp(lkf_vp_state &S, const lkf_vp_params &P, float x, flo
             ax = __ddiv_rn(ax, (double)c); ay = __ddiv_rn(ay, (double)c);
             S.vp_x = __dadd_rn(S.vp_x, __dmul_rn(ax, P.vp_update_rate));
             S.vp_y = __dadd_rn(S.vp_y, __dmul_rn(ay, P.vp_update_rate));
+            S.vp_moved = 1;                                    // Point.update sets _moved (VP.py:180)
             if (S.n_rows < row_cap) { rows[2 * S.n_rows] = S.vp_x; rows[2 * S.n_rows + 1] = S.vp_y; S.n_rows++; }
             else S.row_overflow = 1;
             S.vp_ult = 0;
@@ -86,6 +89,7 @@ __device__ void consume_cp(lkf_vp_state &S, const lkf_vp_params &P, float x, flo
         S.vp_x = __ddiv_rn(ax, (double)R); S.vp_y = __ddiv_rn(ay, (double)R);
         S.ring_alias[slot] = 1;                               // the last CP object BECOMES the VP (B.2)
         S.vp_init = 1;
+        S.vp_moved = 0;                                       // ... an object that was never update()d
         S.vp_ult = 0;
     }
 }
@@ -105,7 +109,8 @@ k_vp_frame(lkf_vp_params P, lkf_vp_state *__restrict__ states, float *__restrict
     double *lens = reinterpret_cast<double *>(tp1 + 4 * maxp);            // [maxp] rounded line lengths of one group
     int *flag = reinterpret_cast<int *>(lens + maxp);                     // [maxp] scratch
     CpRec *cps = reinterpret_cast<CpRec *>(flag + maxp + (maxp & 1));     // [VP_NT] survivors of one pair chunk
-    __shared__ int s_k[2], s_any_none, s_any_one, s_any_zero, s_nl, s_ncp, s_scan[VP_NT / 32];
+    __shared__ int s_k[2], s_any_none, s_any_one, s_any_zero, s_nl, s_ncp, s_scan[VP_NT / 32], s_do_vl;
+    __shared__ double s_red[5][VP_NT / 32], s_mean[2];
     __shared__ lkf_vp_state S;
     if (tid == 0) S = states[b];
     double *rows = rows_all + (size_t)b * row_cap * 2;
@@ -258,16 +263,69 @@ k_vp_frame(lkf_vp_params P, lkf_vp_state *__restrict__ states, float *__restrict
             for (int i = tid; i < 2 * k; i += VP_NT) p0[i] = tp1[g * maxp * 2 + i];       // p0s[n] = good_new
         }
     if (tid == 0) {
+        s_do_vl = 0;
         if (S.vp_init) {
             if (S.vp_ult > P.hide_vp_thold) {
-                S.vp_init = 0; S.ring_count = 0; S.ring_head = 0;
+                S.vp_init = 0; S.ring_count = 0; S.ring_head = 0; S.vp_moved = 0;
                 for (int q = 0; q < LKF_VP_RING; q++) S.ring_alias[q] = 0;
                 if (P.reset_avg_on_hide) { S.avg_len[0] = P.min_fl_len; S.avg_len[1] = P.min_fl_len; }
             } else {
                 if (S.n_rows < row_cap) { rows[2 * S.n_rows] = S.vp_x; rows[2 * S.n_rows + 1] = S.vp_y; S.n_rows++; }
                 else S.row_overflow = 1;
+                s_do_vl = S.vp_moved && P.vl_ref > 0 && !S.row_overflow;      // vl.update(all_vp[-VP_REF:], vp), VP.py:654
             }
         }
+    }
+    __syncthreads();
+    if (s_do_vl) {
+        // VL.update (VP.py:224-245): scipy.stats.linregress slope = (dx.dy / n) / (dx.dx / n) on the de-meaned samples,
+        // intercept = ymean - slope * xmean, for y(x) and for x(y); sums by the CTA (float64, fixed order -> deterministic)
+        const int n = min(S.n_rows, P.vl_ref);
+        const double *h = rows + 2 * (size_t)(S.n_rows - n);
+        const int lane = tid & 31, wid = tid >> 5;
+        auto block_sums = [&](double *v, int cnt) {                       // v[0..cnt) -> s_red[q][0] holds the CTA sums
+            for (int q = 0; q < cnt; q++) {
+                double a = v[q];
+                for (int o = 16; o > 0; o >>= 1) a = __dadd_rn(a, __shfl_down_sync(0xffffffffu, a, o));
+                if (lane == 0) s_red[q][wid] = a;
+            }
+            __syncthreads();
+            if (tid == 0)
+                for (int q = 0; q < cnt; q++) {
+                    double a = s_red[q][0];
+                    for (int w = 1; w < VP_NT / 32; w++) a = __dadd_rn(a, s_red[q][w]);
+                    s_red[q][0] = a;
+                }
+            __syncthreads();
+        };
+        double v[3] = {0.0, 0.0, 0.0};
+        for (int i = tid; i < n; i += VP_NT) { v[0] = __dadd_rn(v[0], h[2 * i]); v[1] = __dadd_rn(v[1], h[2 * i + 1]); }
+        block_sums(v, 2);
+        if (tid == 0) { s_mean[0] = __ddiv_rn(s_red[0][0], (double)n); s_mean[1] = __ddiv_rn(s_red[1][0], (double)n); }
+        __syncthreads();
+        const double xm = s_mean[0], ym = s_mean[1];
+        v[0] = v[1] = v[2] = 0.0;
+        for (int i = tid; i < n; i += VP_NT) {
+            const double dx = __dsub_rn(h[2 * i], xm), dy = __dsub_rn(h[2 * i + 1], ym);
+            v[0] = __fma_rn(dx, dx, v[0]); v[1] = __fma_rn(dx, dy, v[1]); v[2] = __fma_rn(dy, dy, v[2]);
+        }
+        block_sums(v, 3);
+        if (tid == 0) {
+            const double nn = (double)n;
+            const double sxx = __ddiv_rn(s_red[0][0], nn), sxy = __ddiv_rn(s_red[1][0], nn), syy = __ddiv_rn(s_red[2][0], nn);
+            const double m = __ddiv_rn(sxy, sxx), mv = __ddiv_rn(sxy, syy);
+            S.vl_m = m; S.vl_b = __dsub_rn(ym, __dmul_rn(m, xm));
+            S.vl_mv = mv; S.vl_bv = __dsub_rn(xm, __dmul_rn(mv, ym));
+            const double bx = S.vp_x, by = S.vp_y, Wm1 = (double)(mW - 1), Hm1 = (double)(mH - 1);
+            S.vl_bp[0] = bx; S.vl_bp[1] = by;
+            S.vl_lp_y = __dsub_rn(by, __dmul_rn(bx, m));
+            S.vl_rp_y = __dadd_rn(by, __dmul_rn(__dsub_rn(Wm1, bx), m));
+            S.vl_up_x = __dsub_rn(bx, __dmul_rn(by, mv));
+            S.vl_dp_x = __dadd_rn(bx, __dmul_rn(__dsub_rn(Hm1, by), mv));
+            S.vl_init = 1;
+        }
+    }
+    if (tid == 0) {
         counts[2 * b] = k0; counts[2 * b + 1] = k1;
         S.refresh = 0;
         if ((double)(k0 + k1) < P.tp_refresh_below || S.tp_ult == P.tp_update_time) { S.tp_ult = 0; S.refresh = 1; }

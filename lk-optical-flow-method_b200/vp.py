@@ -4,7 +4,7 @@ clips in lock-step, device resident, no host synchronisation per frame.
 Per frame (all clips at once, a fixed launch sequence suitable for a CUDA graph):
     resize (INTER_AREA, VP.py:531) -> process_img (a1+a2) -> pyramid (a3) -> pyramidal LK for both point
     groups (a4+a7) -> vp_frame kernel (a8-a12: ROI filter, flow lines, cross points, VP state machine, CSV rows,
-    refresh decision) -> goodFeaturesToTrack with the 4 ROI sub-masks, executed on the device only for the clips
+    refresh decision, and the vanishing-line pair of class VL, VP.py:196-250) -> goodFeaturesToTrack with the 4 ROI sub-masks, executed on the device only for the clips
     whose refresh flag is set (a5+a6) -> REPlace of the point groups (VP.py:713-715).
 The previous frame's pyramid is kept (ping-pong), so every frame is converted and down-sampled once.
 
@@ -26,7 +26,7 @@ from .device import Workspace, image_desc, pyramid_shapes, stream_ptr
 # module constants of VP.py:21-57 ; LK_Final.py differences per SURVEY Appendix C
 DEFAULTS = dict(WID=860, TP_NUM=20, VP_REF_NUM=10, VP_UPDATE_RATE=0.5, FL_UPDATE_RATE=0.05, TP_UPDATE_RATE=0.3,
                 TP_UPDATE_TIME=10, MIN_ANG_DIF=25, MAX_CP_STD=1.0, MIN_FL_LEN=1.0, CP_THOLD=1 / 15, HIDE_VP_THOLD=50,
-                START_X_FILTER=True, RESET_AVG_ON_HIDE=True)
+                START_X_FILTER=True, RESET_AVG_ON_HIDE=True, VP_REF=300)
 LKF_OVERRIDES = dict(VP_REF_NUM=15, MIN_FL_LEN=1.5, START_X_FILTER=False, RESET_AVG_ON_HIDE=False)
 LK_PARAMS = dict(winSize=(15, 15), maxLevel=2, criteria=(ops.TERM_CRITERIA_EPS | ops.TERM_CRITERIA_COUNT, 10, 0.03))
 
@@ -72,6 +72,30 @@ def csv_text(rows):
     wr.writerow(["x", "y"])
     wr.writerows([(np.float64(x), np.float64(y)) for x, y in rows])
     return buf.getvalue()
+
+
+VL_FIELDS = ("m", "intercept", "mv", "interceptv", "bp_x", "bp_y", "lp_y", "rp_y", "up_x", "dp_x")
+
+
+def vl_of_state(s):
+    """The vanishing-line pair held in an LkfVpState (class VL, VP.py:196-250) as a dict keyed by VL_FIELDS, or None
+    while the clip's VL object is not initialised (the VP has not moved yet)."""
+    if not s.vl_init:
+        return None
+    return dict(m=s.vl_m, intercept=s.vl_b, mv=s.vl_mv, interceptv=s.vl_bv, bp_x=s.vl_bp[0], bp_y=s.vl_bp[1],
+                lp_y=s.vl_lp_y, rp_y=s.vl_rp_y, up_x=s.vl_up_x, dp_x=s.vl_dp_x)
+
+
+def vanishing_lines(vl, WID, Hei, mode="best_point"):
+    """VL.__call__ (VP.py:213-221, 245-250): (left, right, up, down, st) end points of the two lines; all None
+    before the first update.  mode 'best_point': the fitted slopes through the current VP; otherwise the fitted
+    lines themselves.  st is True once initialised (the script's `is not nan` test compares identity)."""
+    if vl is None:
+        return None, None, None, None, None
+    if mode == "best_point":
+        return (0, vl["lp_y"]), (WID - 1, vl["rp_y"]), (vl["up_x"], 0), (vl["dp_x"], Hei - 1), True
+    return ((0, vl["intercept"]), (WID - 1, vl["intercept"] + (WID - 1) * vl["m"]), (vl["interceptv"], 0),
+            (vl["interceptv"] + (Hei - 1) * vl["mv"], Hei - 1), True)
 
 
 def save_csv(rows, video_name, out_dir="./vps"):
@@ -131,7 +155,8 @@ class ClipBatchRunner:
             tp_refresh_below=cfg["TP_NUM"] * cfg["TP_UPDATE_RATE"],
             start_x_sep=float(np.float32(self.WID * 0.05)) if cfg["START_X_FILTER"] else -1.0,
             vp_ref_num=int(cfg["VP_REF_NUM"]), hide_vp_thold=int(cfg["HIDE_VP_THOLD"]),
-            reset_avg_on_hide=1 if cfg["RESET_AVG_ON_HIDE"] else 0, tp_update_time=int(cfg["TP_UPDATE_TIME"]), reserved=0)
+            reset_avg_on_hide=1 if cfg["RESET_AVG_ON_HIDE"] else 0, tp_update_time=int(cfg["TP_UPDATE_TIME"]),
+            vl_ref=int(cfg["VP_REF"]))
         self.frames_done = 0
         self._graphs = [None, None]
         self._graph_in = None
@@ -217,6 +242,10 @@ class ClipBatchRunner:
                 raise RuntimeError(f"clip {b}: CSV row capacity {self.row_cap} exceeded; pass a larger row_capacity")
             out.append(rows[b, :s.n_rows].copy())
         return out
+
+    def vl_host(self):
+        """Per clip: the current vanishing-line pair (dict keyed by VL_FIELDS) or None.  Synchronises."""
+        return [vl_of_state(s) for s in self.state_structs()]
 
     def tracks_host(self):
         """Current point groups per clip: list of (group0 (K,1,2), group1 (K,1,2)) float32 arrays."""

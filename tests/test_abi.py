@@ -22,7 +22,8 @@ def test_header_symbols_exported_and_typed():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
-    assert lib.lkf_abi_version() == 1
+    hdr = open(os.path.join(ROOT, "include", "lkflow_b200.h")).read()
+    assert lib.lkf_abi_version() == int(re.search(r"#define LKF_ABI_VERSION (\d+)", hdr).group(1)) == _lib.ABI_VERSION
     assert lib.lkf_strerror(0) == b"ok" and lib.lkf_strerror(-1) == b"bad argument"
 
 
@@ -32,6 +33,11 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.LkfLkParams) == 6 * 4 + 2 * 8
     assert ctypes.sizeof(_lib.LkfGfttParams) == 4 * 4 + 2 * 8
     assert _lib.LkfLkParams.epsilon.offset == 24 and _lib.LkfGfttParams.quality_level.offset == 16
+    # the compiled structs (host arithmetic inside the library) agree with the ctypes mirrors
+    lib = _lib.load()
+    for which, cls in enumerate((_lib.LkfImage, _lib.LkfLkParams, _lib.LkfGfttParams, _lib.LkfVpParams, _lib.LkfVpState)):
+        assert lib.lkf_struct_size(which) == ctypes.sizeof(cls), cls.__name__
+    assert lib.lkf_struct_size(99) == -1
 
 
 def test_pure_host_entry_points():

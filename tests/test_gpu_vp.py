@@ -2,7 +2,8 @@
 
   * vp_frame kernel vs oracle/vp_oracle.vp_frame on identical synthetic tracks: CSV rows bit-identical (float64),
     surviving point groups identical -- exercises the checkInside dtype flip (B.1), init aliasing (B.2), the
-    +-1 sigma update (B.3), hide/reset (B.4);
+    +-1 sigma update (B.3), hide/reset (B.4); the vanishing-line pair (class VL) after every frame within 1e-6 px
+    (two least-squares fits over <= 300 rows: the CTA's summation order differs from numpy's);
   * ClipBatchRunner (resize -> ... -> CSV) vs the oracle-driven frame loop on a synthetic zoom clip, and against
     the golden CSV written by the UNMODIFIED reference script (tolerance: VP within 1 px, north_star).
 """
@@ -17,6 +18,18 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _check_vl(state, want, where):
+    """state: LkfVpState; want: the oracle's S["vl"] (dict or None).  Slopes to 1e-9 relative, end points to 1e-6 px."""
+    from lk_optical_flow_method_b200 import vp as V
+    got = V.vl_of_state(state)
+    assert (got is None) == (want is None), where
+    if want is None:
+        return 0
+    for k in V.VL_FIELDS:
+        assert np.isclose(got[k], want[k], rtol=1e-9, atol=1e-6, equal_nan=True), (where, k, got[k], want[k])
+    return 1
 
 
 def _masks():
@@ -55,6 +68,7 @@ def test_vp_frame_kernel_matches_oracle(variant, tp_num, seed):
     rng = np.random.default_rng(seed)
     maxp = r.maxp
     md = V.image_desc(r.mask)
+    n_vl = 0
     for f in range(frames):
         quiet = 60 <= f < 125 and seed == 3                       # long gap: exercises the hide/reset path
         P0 = np.zeros((B, 2, maxp, 2), np.float32)
@@ -118,6 +132,9 @@ def test_vp_frame_kernel_matches_oracle(variant, tp_num, seed):
                                      ref=(len(S[b]["rows"]), S[b]["n_lines"], S[b]["n_cps"], S[b]["vp"], S[b]["avg"])), fh)
             assert sts[b].n_rows == len(S[b]["rows"]), (f, b, sts[b].n_rows, len(S[b]["rows"]), sts[b].n_lines, S[b]["n_lines"],
                                                          sts[b].n_cps, S[b]["n_cps"], host_tracks[b])
+            n_vl += _check_vl(sts[b], S[b]["vl"], (f, b))
+            assert bool(sts[b].vp_moved) == bool(S[b]["moved"])
+    assert n_vl > 50                                               # the VL path actually ran
     got = r.rows_host()
     states = r.state_structs()
     total = 0
@@ -177,6 +194,21 @@ def test_clip_runner_vs_oracle_loop_and_golden(oracle, name):
     assert rows[0].shape == gold.shape, (rows[0].shape, gold.shape)
     if len(gold):
         assert np.abs(rows[0] - gold).max() <= 1.0
+    # vanishing-line pair after the last frame: against the oracle loop (same rows -> same fits) and against the state
+    # of the unmodified script's own `vl` object (tests/golden/vl_*.npz; its rows differ by the cv2-vs-oracle LK
+    # difference, so end points within 1 px like the VP itself)
+    st = runner.state_structs()
+    assert _check_vl(st[0], ref["vl"], name) == (1 if ref["vl"] is not None else 0)
+    assert _check_vl(st[1], ref["vl"], name) == (1 if ref["vl"] is not None else 0)
+    z = np.load(os.path.join(GOLD, f"vl_{name}.npz"))
+    assert len(z["rows"]) == len(ref["vl_rows"]) == meta["vl_calls"]
+    if len(z["rows"]) and not np.isnan(z["rows"][-1, 0]):
+        got = V.vl_of_state(st[0])
+        last = dict(zip([str(k) for k in z["fields"]], z["rows"][-1]))
+        assert abs(got["bp_x"] - last["bp_x"]) <= 1.0 and abs(got["bp_y"] - last["bp_y"]) <= 1.0
+        lp, rp, up, dp, ok = V.vanishing_lines(got, runner.WID, runner.Hei)
+        assert ok and lp[0] == 0 and rp[0] == runner.WID - 1 and up[1] == 0 and dp[1] == runner.Hei - 1
+        assert got["lp_y"] == got["bp_y"] - got["bp_x"] * got["m"]
 
 
 def test_c5_batch_of_1080p_clips_sharded_with_csv(oracle, tmp_path):
