@@ -79,6 +79,92 @@ k_resize_area_bgr4(const uint8_t *__restrict__ src, long long srp, long long sip
     o[2] = (uint8_t)(rr < 0.f ? 0.f : (rr > 255.f ? 255.f : rr));
 }
 
+// Column-strip form of the above (4-byte aligned source rows): a thread owns one destination column and walks down
+// RS_ROWS destination rows.  Every source row is loaded and reduced horizontally ONCE (a row that straddles two
+// destination rows feeds both, cv2 recomputes it), as four aligned 32-bit words realigned by funnel shifts; bytes go to
+// float by one PRMT (byte | 0x4B000000) and one subtraction.  Table entries a pixel does not have carry alpha = 0:
+// adding +0 leaves the non-negative partial sums unchanged, so the float32 sequence is the one of cv2.
+constexpr int RS_ROWS = 16;
+
+// cv2's saturate_cast<uchar>(float): round half to even, clamp to [0, 255] -- one conversion instruction
+__device__ __forceinline__ uint8_t sat_u8(float v)
+{
+    unsigned r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return (uint8_t)r;
+}
+
+__device__ __forceinline__ float byte_f32(uint32_t w, int k)      // byte k of w as float, exact
+{
+    const uint32_t sel = k == 0 ? 0x7540u : (k == 1 ? 0x7541u : (k == 2 ? 0x7542u : 0x7543u));
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+}
+
+__global__ void __launch_bounds__(128)
+k_resize_area_bgr4_strip(const uint8_t *__restrict__ src, long long srp, long long sip, uint8_t *__restrict__ dst, long long drp,
+                         long long dip, int Hd, int Wd, const int *__restrict__ xofs, const int *__restrict__ xsi,
+                         const float *__restrict__ xal, const int *__restrict__ yofs, const int *__restrict__ ysi,
+                         const float *__restrict__ yal)
+{
+    const int dx = blockIdx.x * 128 + threadIdx.x, b = blockIdx.z;
+    if (dx >= Wd) return;
+    const int dy0 = blockIdx.y * RS_ROWS, dy1 = min(Hd, dy0 + RS_ROWS);
+    const uint8_t *S = src + (long long)b * sip;
+    const int x0 = __ldg(xofs + dx), nx = __ldg(xofs + dx + 1) - x0;
+    float xa[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) xa[k] = k < nx ? __ldg(xal + x0 + k) : 0.f;
+    const int byte0 = 3 * __ldg(xsi + x0), a0 = byte0 & ~3, sh = (byte0 & 3) * 8;
+    // the 16 bytes read per row must stay inside the row pitch (threads at the right edge take the byte path)
+    const bool words = a0 + 16 <= srp;
+    uint8_t *o = dst + (long long)b * dip + (long long)dy0 * drp + 3 * dx;
+    float sb = 0.f, sg = 0.f, sr = 0.f;
+    int dy = dy0;
+    int j = __ldg(yofs + dy0), jn = __ldg(yofs + dy0 + 1);       // jn: one past the last table entry of destination row dy
+    bool first = true;                                           // next entry opens a destination row
+    const int jend = __ldg(yofs + dy1);
+    // area down-scaling uses every source row once, in order, and a source row feeds at most two destination rows:
+    // walk the source rows sy0..sy1 with a running pointer and hand each reduced row to its one or two table entries
+    const int sy0 = __ldg(ysi + j), sy1 = __ldg(ysi + jend - 1);
+    const uint8_t *row = S + (long long)sy0 * srp;
+    int sy_next = sy0;
+    float ya = __ldg(yal + j);
+    for (int sy = sy0; sy <= sy1; sy++, row += srp) {
+        float v[12];
+        if (words) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(row + a0);
+            const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+            const uint32_t w0 = __funnelshift_r(q0, q1, sh), w1 = __funnelshift_r(q1, q2, sh), w2 = __funnelshift_r(q2, q3, sh);
+#pragma unroll
+            for (int t = 0; t < 4; t++) { v[t] = byte_f32(w0, t); v[4 + t] = byte_f32(w1, t); v[8 + t] = byte_f32(w2, t); }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 12; t++) v[t] = t < 3 * nx ? u8_to_f32(row[byte0 + t]) : 0.f;
+        }
+        float bb = 0.f, bg = 0.f, br = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            bb = __fadd_rn(bb, __fmul_rn(v[3 * k], xa[k]));
+            bg = __fadd_rn(bg, __fmul_rn(v[3 * k + 1], xa[k]));
+            br = __fadd_rn(br, __fmul_rn(v[3 * k + 2], xa[k]));
+        }
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            if (sy_next != sy) break;
+            const float tb = __fmul_rn(ya, bb), tg = __fmul_rn(ya, bg), tr = __fmul_rn(ya, br);
+            if (first) { sb = tb; sg = tg; sr = tr; first = false; }
+            else { sb = __fadd_rn(sb, tb); sg = __fadd_rn(sg, tg); sr = __fadd_rn(sr, tr); }
+            j++;
+            if (j == jn) {
+                o[0] = sat_u8(sb); o[1] = sat_u8(sg); o[2] = sat_u8(sr);
+                o += drp; dy++; first = true;
+                if (dy < dy1) jn = __ldg(yofs + dy + 1);
+            }
+            if (j < jend) { sy_next = __ldg(ysi + j); ya = __ldg(yal + j); } else sy_next = -1;
+        }
+    }
+}
+
 }  // namespace
 
 LKF_EXPORT int lkf_resize_area_u8(const lkf_image *src, const lkf_image *dst, const int32_t *xofs, const int32_t *xsi,
@@ -93,6 +179,14 @@ LKF_EXPORT int lkf_resize_area_u8(const lkf_image *src, const lkf_image *dst, co
     if (src->width % dst->width == 0 && src->height % dst->height == 0) return LKF_ERR_UNSUPPORTED;  // cv2's integer fast path
     dim3 grid((dst->width + 63) / 64, (dst->height + 3) / 4, dst->batch);
     // horizontal footprint of a destination pixel: at most floor(scale) + 2 table entries
+    if (src->channels == 3 && 2LL * src->width < 5LL * dst->width && aligned_to(src, 4) && src->row_pitch >= 16) {
+        dim3 g((dst->width + 127) / 128, (dst->height + RS_ROWS - 1) / RS_ROWS, dst->batch);
+        k_resize_area_bgr4_strip<<<g, 128, 0, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch,
+                                                                      (uint8_t *)dst->data, dst->row_pitch, dst->image_pitch,
+                                                                      dst->height, dst->width, xofs, xsi, xalpha, yofs, ysi, yalpha);
+        LKF_LAUNCH_CHECK(nullptr);
+        return LKF_OK;
+    }
     if (src->channels == 3 && 2LL * src->width < 5LL * dst->width) {      // scale < 2.5 -> at most 4 table entries per pixel
         k_resize_area_bgr4<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch,
                                                                   (uint8_t *)dst->data, dst->row_pitch, dst->image_pitch, dst->height,

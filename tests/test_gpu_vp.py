@@ -161,6 +161,16 @@ def test_resize_area_bit_exact(oracle):
         assert np.array_equal(got, np.stack([oracle.resize_area(x, (wd, hd)) for x in f]))
     g = torch.from_numpy(np.ascontiguousarray(f[..., 1])).cuda()
     assert np.array_equal(ops.resize_area(g, (215, 120)).cpu().numpy(), np.stack([oracle.resize_area(x, (215, 120)) for x in f[..., 1]]))
+    # the scripts' own geometries (VP.py:430-433): 1280x720 and 1920x1080 frames to WID = 860 (column-strip kernel,
+    # word loads; the last columns take its byte path), and a crop whose rows are not 4-byte aligned (per-pixel kernel)
+    for (W, H) in [(1280, 720), (1920, 1080)]:
+        tex2 = synth.make_texture(W, H, 5)
+        fr = np.stack([synth.zoom_frame(tex2, W, H, t) for t in (1, 4)])
+        got = ops.resize_area(torch.from_numpy(fr).cuda(), (860, 483)).cpu().numpy()
+        assert np.array_equal(got, np.stack([oracle.resize_area(x, (860, 483)) for x in fr])), (W, H)
+    crop = torch.from_numpy(fr).cuda()[:, 3:723, 5:1286]                 # 1281 x 720 view, pitch 5760, base offset 15 bytes
+    want = np.stack([oracle.resize_area(np.ascontiguousarray(x), (860, 483)) for x in fr[:, 3:723, 5:1286]])
+    assert np.array_equal(ops.resize_area(crop, (860, 483)).cpu().numpy(), want)
 
 
 def _clip(meta, n):

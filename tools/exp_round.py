@@ -1,6 +1,6 @@
 """Tuning experiment (one process per setting: the switches are read once): LK stage and pyramid stage timings of the
 bench workload under LKF_LK_VARIANT / LKF_LK_PERSIST / LKF_PD_ROWS, with a checksum of the outputs.
-Usage: exp_round.py lk|pyr [B]"""
+Usage: exp_round.py lk|pyr|resize [B]"""
 import hashlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -46,6 +46,12 @@ if what == "lk":
     us = timeit(pipe.stage_track)
     outs = [getattr(pipe, n) for n in ("next_pts", "status", "err") if hasattr(pipe, n)]
     print(f"[{tag}] lk stage {us:8.1f} us per {B} pairs  digest {digest(*outs) if outs else '-'}")
+elif what == "resize":
+    for (h, w) in ((1080, 1920), (720, 1280)):
+        src = frames[:, :h, :w].contiguous()
+        out = ops.resize_area(src, (860, 483))
+        us = timeit(lambda: ops.resize_area(src, (860, 483), out=out))
+        print(f"[{tag}] resize_area {w}x{h} -> 860x483: {us:7.1f} us per {B + 1} frames ({src.numel() / us / 1e6:6.2f} TB/s read)  digest {digest(out)}")
 else:
     l1 = ops.pyr_down(gray); l2 = ops.pyr_down(l1)
     a = timeit(lambda: ops.pyr_down(gray, out=l1)); b = timeit(lambda: ops.pyr_down(l1, out=l2))
