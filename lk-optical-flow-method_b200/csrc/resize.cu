@@ -94,10 +94,13 @@ __device__ __forceinline__ uint8_t sat_u8(float v)
     return (uint8_t)r;
 }
 
-__device__ __forceinline__ float byte_f32(uint32_t w, int k)      // byte k of w as float, exact
+// byte k of w as the float 2^23 + byte (exact).  The product byte * alpha rounded to float32 -- cv2's
+// `S[sx] * alpha` -- is then ONE fused multiply-add: fma(2^23 + byte, alpha, -(2^23 * alpha)); 2^23 * alpha is exact,
+// so the single rounding applies to the exact value byte * alpha.
+__device__ __forceinline__ float byte_biased(uint32_t w, int k)
 {
     const uint32_t sel = k == 0 ? 0x7540u : (k == 1 ? 0x7541u : (k == 2 ? 0x7542u : 0x7543u));
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel));
 }
 
 __global__ void __launch_bounds__(128)
@@ -111,9 +114,9 @@ k_resize_area_bgr4_strip(const uint8_t *__restrict__ src, long long srp, long lo
     const int dy0 = blockIdx.y * RS_ROWS, dy1 = min(Hd, dy0 + RS_ROWS);
     const uint8_t *S = src + (long long)b * sip;
     const int x0 = __ldg(xofs + dx), nx = __ldg(xofs + dx + 1) - x0;
-    float xa[4];
+    float xa[4], xc[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) xa[k] = k < nx ? __ldg(xal + x0 + k) : 0.f;
+    for (int k = 0; k < 4; k++) { xa[k] = k < nx ? __ldg(xal + x0 + k) : 0.f; xc[k] = -8388608.0f * xa[k]; }
     const int byte0 = 3 * __ldg(xsi + x0), a0 = byte0 & ~3, sh = (byte0 & 3) * 8;
     // the 16 bytes read per row must stay inside the row pitch (threads at the right edge take the byte path)
     const bool words = a0 + 16 <= srp;
@@ -130,23 +133,24 @@ k_resize_area_bgr4_strip(const uint8_t *__restrict__ src, long long srp, long lo
     int sy_next = sy0;
     float ya = __ldg(yal + j);
     for (int sy = sy0; sy <= sy1; sy++, row += srp) {
-        float v[12];
+        float v[12];                                   // 2^23 + byte
         if (words) {
             const uint32_t *q = reinterpret_cast<const uint32_t *>(row + a0);
             const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
             const uint32_t w0 = __funnelshift_r(q0, q1, sh), w1 = __funnelshift_r(q1, q2, sh), w2 = __funnelshift_r(q2, q3, sh);
 #pragma unroll
-            for (int t = 0; t < 4; t++) { v[t] = byte_f32(w0, t); v[4 + t] = byte_f32(w1, t); v[8 + t] = byte_f32(w2, t); }
+            for (int t = 0; t < 4; t++) { v[t] = byte_biased(w0, t); v[4 + t] = byte_biased(w1, t); v[8 + t] = byte_biased(w2, t); }
         } else {
 #pragma unroll
-            for (int t = 0; t < 12; t++) v[t] = t < 3 * nx ? u8_to_f32(row[byte0 + t]) : 0.f;
+            for (int t = 0; t < 12; t++) v[t] = __uint_as_float(0x4B000000u | (t < 3 * nx ? (uint32_t)row[byte0 + t] : 0u));
         }
-        float bb = 0.f, bg = 0.f, br = 0.f;
+        // buf = ((s0 a0 + s1 a1) + s2 a2) + s3 a3 per channel (cv2 starts from 0: 0 + s0 a0 = s0 a0)
+        float bb = __fmaf_rn(v[0], xa[0], xc[0]), bg = __fmaf_rn(v[1], xa[0], xc[0]), br = __fmaf_rn(v[2], xa[0], xc[0]);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            bb = __fadd_rn(bb, __fmul_rn(v[3 * k], xa[k]));
-            bg = __fadd_rn(bg, __fmul_rn(v[3 * k + 1], xa[k]));
-            br = __fadd_rn(br, __fmul_rn(v[3 * k + 2], xa[k]));
+        for (int k = 1; k < 4; k++) {
+            bb = __fadd_rn(bb, __fmaf_rn(v[3 * k], xa[k], xc[k]));
+            bg = __fadd_rn(bg, __fmaf_rn(v[3 * k + 1], xa[k], xc[k]));
+            br = __fadd_rn(br, __fmaf_rn(v[3 * k + 2], xa[k], xc[k]));
         }
 #pragma unroll
         for (int rep = 0; rep < 2; rep++) {
