@@ -280,7 +280,7 @@ def run_reference(args):
                              "variants": r["variants"]},
             "e2e": {"value": v, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -500,11 +500,30 @@ def run_b200(args):
                 "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
                 "roofline": roof, "roofline_hbm_stencil": roof_hbm, "stages": stages,
                 "fp32_peak_tflops_measured": fp32_peak, "cpu_baseline": cpu, "clocks": clk}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_JSON_FD = None
+
+
+def _quiet_stdout():
+    """stdout carries exactly ONE JSON line: anything a library prints to fd 1 on the way (NCCL's version banner at
+    communicator creation, torch.distributed.run notices) is sent to stderr; emit() writes to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
 
 
 def main():
@@ -520,6 +539,7 @@ def main():
     args = ap.parse_args()
     if args.cpu_worker:
         return cpu_worker(args.cpu_worker, args.cpu_seconds)
+    _quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
