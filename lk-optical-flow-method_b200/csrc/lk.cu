@@ -369,6 +369,13 @@ __device__ __forceinline__ void place_tile(int ix, int iy, int W, int H, int &tx
     if (iy >= 0 && iy + WH1 <= H && H >= T::TH) ty0 = min(max(ty0, 0), H - T::TH);
 }
 
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Loads NROWS x NWORDS 32-bit words (rows gy0.., columns from the 4-aligned gx0) of a 4-byte aligned plane into `dst`
 // (pitch NWORDS words): LPR lanes per row, 32/LPR rows per pass, all loads issued before the first store (one memory
 // round trip).  Rows outside the level are mirrored (REFLECT_101); a word that straddles the left/right border is
@@ -385,19 +392,12 @@ __device__ __noinline__ void load_words_edge(const uint8_t *__restrict__ P, long
 #pragma unroll 1
     for (int r = r0; r < NROWS; r += RPP) {
         const uint8_t *row = P + (long long)reflect101(gy0 + r, H) * rp;
-        uint32_t v;
-        if (word_ok) v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
-        else v = (uint32_t)row[x0] | ((uint32_t)row[x1] << 8) | ((uint32_t)row[x2] << 16) | ((uint32_t)row[x3] << 24);
-        dst[r * NWORDS + k] = v;
+        // words inside the row: asynchronous copy like the interior path (the caller commits and waits); only a word
+        // that straddles the left / right border is assembled from mirrored bytes
+        if (word_ok) cp_async4(dst + r * NWORDS + k, row + gx);
+        else dst[r * NWORDS + k] = (uint32_t)row[x0] | ((uint32_t)row[x1] << 8) | ((uint32_t)row[x2] << 16) | ((uint32_t)row[x3] << 24);
     }
 }
-
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ASYNCHRONOUS: the interior path issues cp.async copies (global -> shared, no registers, no stall); the caller commits
 // the group and waits (cp_async_wait + __syncwarp) before reading.  The cold border path loads synchronously.
