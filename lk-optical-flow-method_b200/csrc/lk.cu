@@ -465,31 +465,73 @@ template <class T>
 __device__ __noinline__ void template_border(const unsigned char *raw, int ro, short2 *der, unsigned char *tpl, int ipx, int ipy,
                                              int W, int H, int w00, int w01, int w10, int w11, int lane)
 {
+    // 1. Scharr at the sample grid, four samples of a row per step: the six raw bytes under them come from three aligned
+    //    words per row (funnel-shifted), column terms first (V = [3 10 3] down the rows, Dv = bottom - top)
+    constexpr int SEG = 4, SPR = (T::DW + SEG - 1) / SEG;
 #pragma unroll 1
-    for (int idx = lane; idx < T::DW * T::DH; idx += 32) {
-        const int j = idx / T::DW, i = idx - j * T::DW;
-        const unsigned char *r0 = raw + j * T::RWP + ro + i, *r1 = r0 + T::RWP, *r2 = r1 + T::RWP;
-        const int qx = ipx + i, qy = ipy + j;
-        int ix = 0, iy = 0;
-        if (qx >= 0 && qx < W && qy >= 0 && qy < H) {
-            ix = 3 * (r0[2] - r0[0]) + 10 * (r1[2] - r1[0]) + 3 * (r2[2] - r2[0]);
-            iy = 3 * (r2[0] - r0[0]) + 10 * (r2[1] - r0[1]) + 3 * (r2[2] - r0[2]);
+    for (int sg = lane; sg < T::DH * SPR; sg += 32) {
+        const int j = sg / SPR, i0 = (sg - j * SPR) * SEG;
+        const int col = ro + i0, sh = (col & 3) * 8;
+        int V[6], Dv[6];
+        {
+            uint32_t lo[3], hi[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(raw + (j + r) * T::RWP) + (col >> 2);
+                const uint32_t a = q[0], b = q[1], c = q[2];
+                lo[r] = __funnelshift_r(a, b, sh); hi[r] = __funnelshift_r(b, c, sh);
+            }
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                const int t = (int)(((c < 4 ? lo[0] : hi[0]) >> (8 * (c & 3))) & 255u);
+                const int m = (int)(((c < 4 ? lo[1] : hi[1]) >> (8 * (c & 3))) & 255u);
+                const int u = (int)(((c < 4 ? lo[2] : hi[2]) >> (8 * (c & 3))) & 255u);
+                V[c] = 3 * (t + u) + 10 * m; Dv[c] = u - t;
+            }
         }
-        der[j * T::DWP + i] = make_short2((short)ix, (short)iy);
+        const bool row_ok = ipy + j >= 0 && ipy + j < H;
+        short2 *o = der + j * T::DWP + i0;
+#pragma unroll
+        for (int t = 0; t < SEG; t++) {
+            const int qx = ipx + i0 + t;
+            const bool ok = row_ok && qx >= 0 && qx < W;
+            const int ix = ok ? V[t + 2] - V[t] : 0;
+            const int iy = ok ? 3 * (Dv[t] + Dv[t + 2]) + 10 * Dv[t + 1] : 0;
+            if (i0 + t < T::DW) o[t] = make_short2((short)ix, (short)iy);
+        }
     }
     __syncwarp();
+    // 2. the Q14 bilinear patch, run by run like the interior path: I~ by DP2A on the raw bytes, Ix~ / Iy~ from the four
+    //    derivative taps; written in chunks of up to 8 pixels (whole 16-byte slots)
+    constexpr int CH = T::RUN_ <= 8 ? T::RUN_ : 8;
+    const int wT = (w00 & 0xffff) | (w01 << 16), wB = (w10 & 0xffff) | (w11 << 16);
 #pragma unroll 1
-    for (int idx = lane; idx < T::AREA; idx += 32) {
-        const int y = idx / T::WW_, x = idx - y * T::WW_;
-        const unsigned char *r0 = raw + (y + 1) * T::RWP + ro + x + 1, *r1 = r0 + T::RWP;
-        const short2 d00 = der[y * T::DWP + x], d01 = der[y * T::DWP + x + 1], d10 = der[(y + 1) * T::DWP + x],
-                     d11 = der[(y + 1) * T::DWP + x + 1];
-        const int run = y * T::RPR + x / T::RUN_, t = x % T::RUN_;
-        unsigned char *slot = tpl + run * T::TPL_RUN_BYTES;
-        reinterpret_cast<short *>(slot)[t] = (short)descale(r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11, 9);
-        reinterpret_cast<short2 *>(slot + T::TPL_I_BYTES)[t] =
-            make_short2((short)descale(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14),
-                        (short)descale(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14));
+    for (int rr = lane; rr < T::NRUNS; rr += 32) {
+        const int y = rr / T::RPR, x = (rr - y * T::RPR) * T::RUN_;
+        unsigned char *slot = tpl + rr * T::TPL_RUN_BYTES;
+#pragma unroll 1
+        for (int c0 = 0; c0 < T::RUN_; c0 += CH) {
+            int iv[CH];
+            bilinear_run<CH>(raw + (y + 1) * T::RWP, raw + (y + 2) * T::RWP, ro + x + c0 + 1, wT, wB, iv);
+            const short2 *d0 = der + y * T::DWP + x + c0, *d1 = d0 + T::DWP;
+            uint32_t wI[4] = {0u, 0u, 0u, 0u}, wD[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            short2 p0 = d0[0], p1 = d1[0];
+#pragma unroll
+            for (int t = 0; t < CH; t++) {
+                const short2 n0 = d0[t + 1], n1 = d1[t + 1];
+                const int ixv = descale(p0.x * w00 + n0.x * w01 + p1.x * w10 + n1.x * w11, 14);
+                const int iyv = descale(p0.y * w00 + n0.y * w01 + p1.y * w10 + n1.y * w11, 14);
+                if (c0 + t < T::RUN_) {
+                    if (t & 1) wI[t / 2] |= (uint32_t)iv[t] << 16; else wI[t / 2] = (uint32_t)iv[t];
+                    wD[t] = ((uint32_t)ixv & 0xffffu) | ((uint32_t)iyv << 16);
+                }
+                p0 = n0; p1 = n1;
+            }
+            // chunk c0 occupies bytes [2 c0, 2 c0 + 16) of the I part and [4 c0, 4 c0 + 32) of the D part (c0 is 0 or a multiple of 8)
+            *reinterpret_cast<uint4 *>(slot + 2 * c0) = make_uint4(wI[0], wI[1], wI[2], wI[3]);
+            *reinterpret_cast<uint4 *>(slot + T::TPL_I_BYTES + 4 * c0) = make_uint4(wD[0], wD[1], wD[2], wD[3]);
+            if (CH > 4) *reinterpret_cast<uint4 *>(slot + T::TPL_I_BYTES + 4 * c0 + 16) = make_uint4(wD[4], wD[5], wD[6], wD[7]);
+        }
     }
     __syncwarp();
 }
