@@ -134,7 +134,7 @@ k_lk_track(LKLevels lv, int n_levels, int w, int h, int max_count, double eps2, 
         const uint8_t *I = lv.prev[l] + (long long)b * lv.pip[l];
         const uint8_t *J = lv.next[l] + (long long)b * lv.nip[l];
         const long long irp = lv.prp[l], jrp = lv.nrp[l];
-        const float sc = 1.f / (float)(1 << l);
+        const float sc = __int_as_float((127 - l) << 23);          // 2^-l, exact
         float px = __fmul_rn(ppx, sc), py = __fmul_rn(ppy, sc);
         float nx, ny;
         if (l == n_levels - 1) {
@@ -581,7 +581,7 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
     // template neighbourhood of level l -> raw[l & 1]; its position depends only on prevPts, so it is fetched one level
     // ahead (cp.async) and never waited for, except at the top level
     auto issue_raw = [&](int l) {
-        const float sc = 1.f / (float)(1 << l);
+        const float sc = __int_as_float((127 - l) << 23);          // 2^-l, exact
         const float px = __fsub_rn(__fmul_rn(ppx, sc), hx), py = __fsub_rn(__fmul_rn(ppy, sc), hy);
         const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
         if (!out_of_level(px, py, ipx, ipy, WW, WH, lv.W[l], lv.H[l]))
@@ -601,7 +601,7 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, d
         if (tile_pending) { cp_async_wait<0>(); tile_pending = false; }     // a level left early: its tile copy must land first
         __syncwarp();
         if (l > 0) issue_raw(l - 1); else cp_async_commit();
-        const float sc = 1.f / (float)(1 << l);
+        const float sc = __int_as_float((127 - l) << 23);          // 2^-l, exact
         float px = __fmul_rn(ppx, sc), py = __fmul_rn(ppy, sc);
         float nx, ny;
         if (l == n_levels - 1) {
@@ -926,7 +926,7 @@ k_lk_track_small(LKLevels lv, int n_levels, int max_count, double eps2, int flag
         const uint8_t *J = lv.next[l] + (long long)b * lv.nip[l];
         const long long irp = lv.prp[l], jrp = lv.nrp[l];
         const bool jal4 = (al4_mask >> l) & 1u, ial4 = (ial4_mask >> l) & 1u;
-        const float sc = 1.f / (float)(1 << l);
+        const float sc = __int_as_float((127 - l) << 23);          // 2^-l, exact
         float px = __fmul_rn(ppx, sc), py = __fmul_rn(ppy, sc);
         float nx, ny;
         if (l == n_levels - 1) {
