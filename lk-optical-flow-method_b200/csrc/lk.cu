@@ -43,12 +43,25 @@ __device__ __forceinline__ long long warp_sum(long long v)
 
 // cv2: delta.ddot(delta) <= epsilon, the dot product accumulated in double.  A float32 estimate decides all but the
 // borderline cases (relative error of the estimate < 3e-7), which take the exact double path.
-__device__ __forceinline__ bool lk_step_below_eps(float dx, float dy, double eps2)
+// (the float bounds are prepared on the host: kernel parameters cost neither registers nor instructions per iteration)
+struct LKEps {
+    double e2;          // epsilon^2 after cv2's clamping
+    float lo, hi;       // (float)e2 * 0.999999f, (float)e2 * 1.000001f
+};
+static inline LKEps make_eps(double e2)
 {
-    const float f = dx * dx + dy * dy, e = (float)eps2;
-    if (f < e * 0.999999f) return true;
-    if (f > e * 1.000001f) return false;
-    return __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2;
+    LKEps r;
+    r.e2 = e2;
+    const float e = (float)e2;
+    r.lo = e * 0.999999f; r.hi = e * 1.000001f;
+    return r;
+}
+__device__ __forceinline__ bool lk_step_below_eps(float dx, float dy, const LKEps &eps)
+{
+    const float f = dx * dx + dy * dy;
+    if (f < eps.lo) return true;
+    if (f > eps.hi) return false;
+    return __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps.e2;
 }
 // cv2: std::abs(x) < 0.01 with a float x and the double constant 0.01: the largest float below 0.01 is fl(0.01)
 __device__ __forceinline__ bool lk_below_001(float x) { return fabsf(x) <= 0.00999999977648258209228515625f; }
@@ -101,7 +114,7 @@ __device__ __forceinline__ void sweep_J(const uint8_t *__restrict__ J, long long
 
 template <class ACC>
 __global__ void __launch_bounds__(LK_WARPS * 32)
-k_lk_track(LKLevels lv, int n_levels, int w, int h, int max_count, double eps2, int flags, double min_eig_thr,
+k_lk_track(LKLevels lv, int n_levels, int w, int h, int max_count, LKEps eps2, int flags, double min_eig_thr,
            const float *__restrict__ prev_pts, const int *__restrict__ counts, int max_pts,
            float *__restrict__ next_pts, uint8_t *__restrict__ status, float *__restrict__ err,
            int *__restrict__ iters_out, int per_warp_bytes)
@@ -538,7 +551,7 @@ __device__ __noinline__ void template_border(const unsigned char *raw, int ro, s
 
 template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, int MINB>
 __global__ void __launch_bounds__(LKT_WARPS * 32, MINB)
-k_lk_track_t(LKLevels lv, int n_levels, int max_count, double eps2, int flags, double min_eig_thr,
+k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, double min_eig_thr,
              const float *__restrict__ prev_pts, const int *__restrict__ counts, int max_pts,
              float *__restrict__ next_pts, uint8_t *__restrict__ status, float *__restrict__ err,
              int *__restrict__ iters_out, unsigned al4_mask, unsigned ial4_mask)
@@ -828,7 +841,7 @@ int launch_lk_t(const LKLevels &lv, int n_levels, int max_count, double eps, con
     }
     dim3 grid((max_pts + LKT_WARPS - 1) / LKT_WARPS, B);
     k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB><<<grid, LKT_WARPS * 32, smem, s>>>(
-        lv, n_levels, max_count, eps, p->flags, p->min_eig_threshold, prev_pts, pt_counts, max_pts, next_pts, status, err, iters,
+        lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, prev_pts, pt_counts, max_pts, next_pts, status, err, iters,
         al4_mask, ial4_mask);
     return LKF_OK;
 }
@@ -900,7 +913,7 @@ __device__ __forceinline__ void bilinear_packed(const uint32_t (&top)[NW], const
 
 template <int WW, int WH>
 __global__ void __launch_bounds__(128)
-k_lk_track_small(LKLevels lv, int n_levels, int max_count, double eps2, int flags, double min_eig_thr,
+k_lk_track_small(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, double min_eig_thr,
                  const float *__restrict__ prev_pts, const int *__restrict__ counts, int max_pts,
                  float *__restrict__ next_pts, uint8_t *__restrict__ status, float *__restrict__ err,
                  int *__restrict__ iters_out, unsigned al4_mask, unsigned ial4_mask)
@@ -1077,7 +1090,7 @@ int launch_lk_small(const LKLevels &lv, int n_levels, int max_count, double eps,
                     unsigned al4_mask, unsigned ial4_mask, int B, cudaStream_t s)
 {
     dim3 grid((max_pts + 127) / 128, B);
-    k_lk_track_small<WW, WH><<<grid, 128, 0, s>>>(lv, n_levels, max_count, eps, p->flags, p->min_eig_threshold, prev_pts, pt_counts,
+    k_lk_track_small<WW, WH><<<grid, 128, 0, s>>>(lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, prev_pts, pt_counts,
                                                   max_pts, next_pts, status, err, iters, al4_mask, ial4_mask);
     return LKF_OK;
 }
@@ -1150,12 +1163,12 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     if (rc == LKF_OK) { LKF_LAUNCH_CHECK(ctx); return LKF_OK; }
     if (area <= 2048) {      // int32 lane partials cannot overflow (<= 64 px/lane * 8160*4080)
         if (smem > 48 * 1024) LKF_CUDA(cudaFuncSetAttribute(k_lk_track<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_lk_track<int><<<grid, LK_WARPS * 32, smem, s>>>(lv, n_levels, p->win_w, p->win_h, max_count, eps, p->flags,
+        k_lk_track<int><<<grid, LK_WARPS * 32, smem, s>>>(lv, n_levels, p->win_w, p->win_h, max_count, make_eps(eps), p->flags,
                                                           p->min_eig_threshold, prev_pts, pt_counts, max_pts, next_pts,
                                                           status, err, iters, (int)pw);
     } else {
         if (smem > 48 * 1024) LKF_CUDA(cudaFuncSetAttribute(k_lk_track<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_lk_track<long long><<<grid, LK_WARPS * 32, smem, s>>>(lv, n_levels, p->win_w, p->win_h, max_count, eps, p->flags,
+        k_lk_track<long long><<<grid, LK_WARPS * 32, smem, s>>>(lv, n_levels, p->win_w, p->win_h, max_count, make_eps(eps), p->flags,
                                                                 p->min_eig_threshold, prev_pts, pt_counts, max_pts,
                                                                 next_pts, status, err, iters, (int)pw);
     }
