@@ -62,3 +62,25 @@ def test_pyramid_shapes():
     from lk_optical_flow_method_b200.device import pyramid_shapes
     assert pyramid_shapes(483, 860, 3) == [(483, 860), (242, 430), (121, 215)]
     assert pyramid_shapes(1080, 1920, 3) == [(1080, 1920), (540, 960), (270, 480)]
+
+
+def test_vanishing_line_endpoints_match_the_oracle_restatement():
+    """vp.vanishing_lines (host mirror of VL.__call__, VP.py:213-221, 245-250) against oracle.vl_endpoints in both modes,
+    on vanishing-line states recorded from the unmodified script (tests/golden/vl_*.npz)."""
+    import os
+    from conftest import ROOT
+    from lk_optical_flow_method_b200 import vp as V
+    from oracle import vp_oracle as O
+    assert V.VL_FIELDS == O.VL_FIELDS
+    assert V.vanishing_lines(None, 860, 483) == (None, None, None, None, None)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "vl_vp_zoom300.npz"))
+    rows = z["rows"][~np.isnan(z["rows"][:, 0])]
+    assert len(rows) > 100
+    for r in rows[::37]:
+        vl = dict(zip(V.VL_FIELDS, (float(x) for x in r)))
+        for mode in ("best_point", "other"):
+            assert V.vanishing_lines(vl, 860, 483, mode) == O.vl_endpoints(vl, 860, 483, mode)
+        lp, rp, up, dp, st = V.vanishing_lines(vl, 860, 483)
+        # the recorded end points are the script's own (VP.py:241-244)
+        assert st is True and lp == (0, vl["lp_y"]) and rp == (859, vl["rp_y"]) and up == (vl["up_x"], 0) and dp == (vl["dp_x"], 482)
+        assert abs(vl["lp_y"] - (vl["bp_y"] - vl["bp_x"] * vl["m"])) < 1e-9
