@@ -81,9 +81,10 @@ k_resize_area_bgr4(const uint8_t *__restrict__ src, long long srp, long long sip
 
 // Column-strip form of the above (4-byte aligned source rows): a thread owns one destination column and walks down
 // RS_ROWS destination rows.  Every source row is loaded and reduced horizontally ONCE (a row that straddles two
-// destination rows feeds both, cv2 recomputes it), as four aligned 32-bit words realigned by funnel shifts; bytes go to
-// float by one PRMT (byte | 0x4B000000) and one subtraction.  Table entries a pixel does not have carry alpha = 0:
-// adding +0 leaves the non-negative partial sums unchanged, so the float32 sequence is the one of cv2.
+// destination rows feeds both, cv2 recomputes it), as four aligned 32-bit words realigned by funnel shifts; a byte becomes
+// the float 2^23 + byte by one PRMT and its weighted value by one exact FMA (see byte_biased).  Table entries a pixel
+// does not have carry alpha = 0: adding +0 leaves the non-negative partial sums unchanged, so the float32 sequence is
+// the one of cv2.
 constexpr int RS_ROWS = 16;
 
 // cv2's saturate_cast<uchar>(float): round half to even, clamp to [0, 255] -- one conversion instruction
