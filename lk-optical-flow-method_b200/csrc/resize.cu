@@ -1,7 +1,8 @@
 // resize.cu -- "next" row: imutils.resize(frame, width=860) = cv2.resize(..., INTER_AREA) with a
 // non-integer scale (VP.py:433,531; 1280x720 -> 860x483).  Same float32 operation order as cv2's ResizeArea
 // (oracle lko_resize_area): per source row a horizontal weighted sum accumulated in table order,
-// then a vertical weighted accumulation, then round-half-even + saturate.  No FMA contraction.
+// then a vertical weighted accumulation, then round-half-even + saturate.  cv2's multiplies and adds are never
+// contracted (the one FMA of the strip kernel restates conversion + multiply exactly, see byte_biased).
 // The coefficient tables are built on the host (double arithmetic, exactly cv2's computeResizeAreaTab).
 #include "common.cuh"
 
