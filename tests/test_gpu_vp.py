@@ -254,3 +254,23 @@ def test_c5_batch_of_1080p_clips_sharded_with_csv(oracle, tmp_path):
         assert text == V.csv_text(want) and text.startswith("x,y\r\n")
         n_rows += len(want)
     assert n_rows > 0                                   # the VP state machine actually produced rows
+
+
+def test_drop_in_module_in_the_scripts_frame_loop(oracle):
+    """The cv2-signature module (lk_optical_flow_method_b200.cv) used the way the scripts use `cv`: numpy frames in,
+    numpy results out, four masked goodFeaturesToTrack calls per refresh, one calcOpticalFlowPyrLK per point group,
+    `st` mutated in place (VP.py:503, 545-553, 707) -- driven by the restated frame loop.  Same rows as the loop on the
+    oracle's functions, within 1 px of the unmodified script's CSV."""
+    from lk_optical_flow_method_b200 import cv
+    from oracle import vp_oracle as O
+    name = "vp_fast40"
+    meta = json.load(open(os.path.join(GOLD, f"{name}.json")))
+    frames = _clip(meta, meta["frames"])
+    masks = _masks()
+    got = O.run_clip(frames, cv, variant="VP", masks=masks, **meta["overrides"])
+    ref = O.run_clip(frames, oracle.OracleCV, variant="VP", masks=masks, **meta["overrides"])
+    a, b = np.array(got["rows"], np.float64).reshape(-1, 2), np.array(ref["rows"], np.float64).reshape(-1, 2)
+    assert a.shape == b.shape and np.array_equal(a, b)
+    gold = np.loadtxt(os.path.join(GOLD, f"{name}.csv"), delimiter=",", skiprows=1).reshape(-1, 2)
+    assert a.shape == gold.shape and np.abs(a - gold).max() <= 1.0
+    assert O.csv_text(got["rows"]).startswith("x,y\r\n")
