@@ -1,5 +1,6 @@
-"""Tuning experiment (one process per setting: the switches are read once): LK stage and pyramid stage timings of the
-bench workload under LKF_LK_VARIANT / LKF_LK_PERSIST / LKF_PD_ROWS, with a checksum of the outputs.
+"""Per-stage timings of the bench workload with a checksum of the outputs (bit-identity check across builds): the LK
+stage, the two pyrDown levels, the INTER_AREA resize.  Any LKF_* environment variable is echoed in the tag, so a
+temporary tuning switch (read once per process by the library) can be compared run against run.
 Usage: exp_round.py lk|pyr|resize [B]"""
 import hashlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
