@@ -428,7 +428,7 @@ def run_b200(args):
     # ---- FP32 pipe peak probe ------------------------------------------------------------------
     import ctypes
     scratch = torch.zeros(4, device=dev)
-    blocks, it = 148 * 16, 20000
+    blocks, it = 148 * 16, 2000
     from lk_optical_flow_method_b200.device import stream_ptr
     for _ in range(2):
         ws.lib.lkf_probe_fp32_fma(blocks, it, scratch.data_ptr(), stream_ptr())
@@ -437,7 +437,7 @@ def run_b200(args):
     ws.lib.lkf_probe_fp32_fma(blocks, it, scratch.data_ptr(), stream_ptr())
     p1.record()
     torch.cuda.synchronize()
-    fp32_peak = blocks * 256 * it * 16 / (p0.elapsed_time(p1) * 1e-3) / 1e12
+    fp32_peak = blocks * 256 * it * 128 * 2 / (p0.elapsed_time(p1) * 1e-3) / 1e12
 
     # ---- rooflines -------------------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -188,7 +188,10 @@ int lkf_vp_frame(const lkf_vp_params *params, lkf_vp_state *states, int n_clips,
 int lkf_vp_apply_refresh(lkf_vp_state *states, int n_clips, const float *corners, const int32_t *corner_counts,
                          int max_out, float *p0, int32_t *counts, int max_pts_per_group, int force, lkf_stream stream);
 
-/* ---- measurement helper (bench.py): FFMA-rate probe; executes blocks*256*iters*16 flops ------- */
+/* ---- measurement helpers (bench.py): instruction-rate probes of the non-tensor pipes.  lkf_probe_pipe: kind 0 FFMA,
+ *      1 IMAD, 2 IDP.2A (dp2a), 3 SHF+LOP3 pairs, 4 FFMA+SHF pairs, 5 IMAD/SHF, 6 IMAD/FFMA, 7 IDP.2A/SHF/FFMA alternating; each of blocks*256 threads executes iters*128 probe
+ *      instructions (kinds 3, 4: iters*256).  lkf_probe_fp32_fma = kind 0: blocks*256*iters*128*2 flops. ------------- */
+int lkf_probe_pipe(int kind, int blocks, int iters, float *out, lkf_stream stream);
 int lkf_probe_fp32_fma(int blocks, int iters, float *out, lkf_stream stream);
 
 #ifdef __cplusplus

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "liblkflow_b200.so")
+# LKFLOW_B200_SO: developer switch for A/B timing of two builds of the same library (tools/exp_round.py)
+SO_PATH = os.environ.get("LKFLOW_B200_SO") or os.path.join(_HERE, "csrc", "liblkflow_b200.so")
 ABI_VERSION = 2          # LKF_ABI_VERSION of include/lkflow_b200.h
 
 LKF_MAX_LEVELS = 8
@@ -90,6 +91,7 @@ SIGNATURES = {
                               _vp, _vp, _vp, _vp, _vp]),
     "lkf_corner_min_eigen_f32": (_i, [_P(LkfImage), _P(LkfImage), _i, _i, _vp]),
     "lkf_probe_fp32_fma": (_i, [_i, _i, _vp, _vp]),
+    "lkf_probe_pipe": (_i, [_i, _i, _i, _vp, _vp]),
     "lkf_gftt_detect": (_i, [_vp, _P(LkfGfttParams), _P(LkfImage), _P(LkfImage), _i, _vp, _vp, _vp, _i, _vp]),
     "lkf_resize_area_u8": (_i, [_P(LkfImage), _P(LkfImage), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lkf_vp_frame": (_i, [_P(LkfVpParams), _vp, _i, _vp, _vp, _vp, _vp, _i, _P(LkfImage), _vp, _i, _vp, _vp, _vp]),

@@ -34,6 +34,22 @@ int lkf_scratch(lkf_ctx *ctx, int slot, size_t bytes, void **out);
 
 void lkf_count_launch(lkf_ctx *ctx);   // ctx may be NULL -> global counter
 
+// Function attributes (dynamic shared memory size, carveout) are per DEVICE: one flag word per kernel instantiation,
+// bit d = "set on device d".  LKF_FUNC_ATTRS(flags, stmts) runs stmts once per device (benign race: the attribute calls
+// are idempotent, the flag is published after them); cudaFuncSetAttribute is far too slow for the per-launch path.
+#include <atomic>
+#define LKF_FUNC_ATTRS(stmts)                                                         \
+    do {                                                                              \
+        static std::atomic<unsigned long long> done__{0};                             \
+        int dev__ = 0;                                                                \
+        LKF_CUDA(cudaGetDevice(&dev__));                                              \
+        const unsigned long long bit__ = 1ull << (dev__ & 63);                        \
+        if (!(done__.load(std::memory_order_acquire) & bit__)) {                      \
+            stmts;                                                                    \
+            done__.fetch_or(bit__, std::memory_order_release);                        \
+        }                                                                             \
+    } while (0)
+
 // Device-side view of an lkf_image
 struct Img {
     uint8_t *p;

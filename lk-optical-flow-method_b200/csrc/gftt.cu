@@ -363,12 +363,10 @@ template <int BS>
 int launch_min_eigen_stream(lkf_ctx *ctx, const lkf_image *src, const lkf_image *eig, int tail, float s, float s2,
                             const int32_t *enable, MaskSet ms, int n_masks, unsigned *maxkey, cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) {
+    LKF_FUNC_ATTRS({
         LKF_CUDA(cudaFuncSetAttribute(k_min_eigen_stream<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MES<BS>::SMEM));
         LKF_CUDA(cudaFuncSetAttribute(k_min_eigen_stream<BS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr = true;
-    }
+    });
     const int W = src->width, H = src->height, B = src->batch;
     const int warps_x = (W + MES_COLS - 1) / MES_COLS, ctas_x = (warps_x + MES_WARPS - 1) / MES_WARPS;
     // strip height: fill whole waves of resident CTAs (shared memory bounds residency), 8..64 rows per strip
@@ -815,7 +813,8 @@ static int min_eigen_impl(lkf_ctx *ctx, const lkf_image *src, const lkf_image *e
     }
     const int pw = ME_W + bs - 1, ph = ME_H + bs - 1, uw = pw + 2, uh = ph + 2, uws = (uw + 3) & ~3;
     size_t smem = (size_t)3 * ph * ME_W * 8 + (size_t)3 * ph * pw * 4 + (size_t)uh * uws;
-    if (smem > 48 * 1024) LKF_CUDA(cudaFuncSetAttribute(k_min_eigen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 227 * 1024) return LKF_ERR_UNSUPPORTED;
+    LKF_FUNC_ATTRS(LKF_CUDA(cudaFuncSetAttribute(k_min_eigen, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
     dim3 grid((W + ME_W - 1) / ME_W, (H + ME_H - 1) / ME_H, src->batch);
     k_min_eigen<<<grid, ME_NT, smem, (cudaStream_t)stream>>>((const uint8_t *)src->data, src->row_pitch, src->image_pitch, H, W,
                                                             (float *)eig->data, eig->row_pitch, eig->image_pitch, bs,
@@ -897,11 +896,7 @@ static int gftt_passes(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *
     }
     LKF_LAUNCH_CHECK(ctx);
     const size_t ss_smem = (size_t)SS_SMEM_KEYS * 8 + (size_t)SS_MAX_CELLS * 4 + (size_t)SS_SMEM_KEYS * 4 + SS_SMEM_KEYS;
-    static bool ss_attr = false;
-    if (!ss_attr) {
-        LKF_CUDA(cudaFuncSetAttribute(k_sort_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_smem));
-        ss_attr = true;
-    }
+    LKF_FUNC_ATTRS(LKF_CUDA(cudaFuncSetAttribute(k_sort_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_smem)));
     k_sort_select<<<g.lists, SS_NT, ss_smem, s>>>(g.keys, g.ccount, g.cap, W, H, p->max_corners, p->min_distance, g.cs, g.gw,
                                                  g.gh, (unsigned *)g.gaux, (unsigned char *)g.gaux + (size_t)g.lists * g.cap * 4, corners,
                                                  counts, max_out, enable, n_masks, g.maxkey, g.hist, g.top);

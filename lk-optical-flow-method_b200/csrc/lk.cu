@@ -308,9 +308,13 @@ struct LKT {
     static constexpr int DER_ONLY = (DWP * DH * 4 + 15) & ~15, U_BYTES = (UP * UH * 4 + 15) & ~15;
     static constexpr int DER_BYTES = DER_ONLY > U_BYTES ? DER_ONLY : U_BYTES, TILE_BYTES = (TWC * TH + 15) & ~15;
     static constexpr int RAW_BYTES = ((RWP * RH + 15) & ~15) + 16;     // + slack: word loaders read up to 2 words past a run
-    // template patch in shared memory, run-major: per run RUN x int16 (I*32) then RUN x (Ix, Iy) int16 pairs, 16-byte slots
-    static constexpr int TPL_I_BYTES = (RUN * 2 + 15) & ~15, TPL_D_BYTES = (RUN * 4 + 15) & ~15, TPL_RUN_BYTES = TPL_I_BYTES + TPL_D_BYTES;
-    static constexpr int TPL_BYTES = TPL_RUN_BYTES * 32 * RPL;
+    // template patch in shared memory.  A lane owns NPX = RUN * RPL window pixels (q = k * RUN + t); per lane the patch is a
+    // list of 32-bit words holding two int16 each: X[i] = (Ix~(2i), Ix~(2i+1)), Y[i] likewise, then I[i] = (I~(2i), I~(2i+1)).
+    // Stored chunk-major -- 16-byte chunk c of lane i at (c * 32 + i) * 16 -- so the 128-bit loads of a sweep are conflict-free.
+    static constexpr int NPX = RUN * RPL, NPAIR = (NPX + 1) / 2;
+    static constexpr int NW_D = 2 * NPAIR, NW_ALL = 3 * NPAIR;
+    static constexpr int NCH_D = (NW_D + 3) / 4, NCH_ALL = (NW_ALL + 3) / 4;
+    static constexpr int TPL_BYTES = NCH_ALL * 512;
     static constexpr int PER_WARP = DER_BYTES + TILE_BYTES + 2 * RAW_BYTES + TPL_BYTES;      // raw is double-buffered
     static_assert(WW % RUN == 0, "RUN must divide the window width");
     static_assert(AREA <= 2048, "int32 lane partials");
@@ -332,6 +336,15 @@ __device__ __forceinline__ int dp2a_hi(int a, unsigned b, int c)
     asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+struct SweepB { static constexpr bool value = false; };      // a window sweep that accumulates the mismatch vector
+struct SweepErr { static constexpr bool value = true; };     // ... that accumulates sum |J~ - I~|
 
 // Q14 bilinear samples of RUN consecutive pixels whose top-left samples start at byte `col` of the 4-byte aligned
 // rows r0 (upper) and r1 (lower): v[t] = (r0[col+t] w00 + r0[col+t+1] w01 + r1[col+t] w10 + r1[col+t+1] w11 + 2^8) >> 9.
@@ -515,19 +528,21 @@ __device__ __noinline__ void template_border(const unsigned char *raw, int ro, s
     }
     __syncwarp();
     // 2. the Q14 bilinear patch, run by run like the interior path: I~ by DP2A on the raw bytes, Ix~ / Iy~ from the four
-    //    derivative taps; written in chunks of up to 8 pixels (whole 16-byte slots)
+    //    derivative taps; every value is one 16-bit store into the lane's own (zeroed) template words
     constexpr int CH = T::RUN_ <= 8 ? T::RUN_ : 8;
     const int wT = (w00 & 0xffff) | (w01 << 16), wB = (w10 & 0xffff) | (w11 << 16);
+    short *mine = reinterpret_cast<short *>(tpl + lane * 16);
+    auto put = [&](int word, int half, int v) { mine[(word >> 2) * 256 + (word & 3) * 2 + half] = (short)v; };
 #pragma unroll 1
-    for (int rr = lane; rr < T::NRUNS; rr += 32) {
+    for (int k = 0; k < T::RPL; k++) {
+        const int rr = lane + 32 * k;
+        if (rr >= T::NRUNS) break;
         const int y = rr / T::RPR, x = (rr - y * T::RPR) * T::RUN_;
-        unsigned char *slot = tpl + rr * T::TPL_RUN_BYTES;
 #pragma unroll 1
         for (int c0 = 0; c0 < T::RUN_; c0 += CH) {
             int iv[CH];
             bilinear_run<CH>(raw + (y + 1) * T::RWP, raw + (y + 2) * T::RWP, ro + x + c0 + 1, wT, wB, iv);
             const short2 *d0 = der + y * T::DWP + x + c0, *d1 = d0 + T::DWP;
-            uint32_t wI[4] = {0u, 0u, 0u, 0u}, wD[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             short2 p0 = d0[0], p1 = d1[0];
 #pragma unroll
             for (int t = 0; t < CH; t++) {
@@ -535,15 +550,13 @@ __device__ __noinline__ void template_border(const unsigned char *raw, int ro, s
                 const int ixv = descale(p0.x * w00 + n0.x * w01 + p1.x * w10 + n1.x * w11, 14);
                 const int iyv = descale(p0.y * w00 + n0.y * w01 + p1.y * w10 + n1.y * w11, 14);
                 if (c0 + t < T::RUN_) {
-                    if (t & 1) wI[t / 2] |= (uint32_t)iv[t] << 16; else wI[t / 2] = (uint32_t)iv[t];
-                    wD[t] = ((uint32_t)ixv & 0xffffu) | ((uint32_t)iyv << 16);
+                    const int q = k * T::RUN_ + c0 + t;
+                    put(q >> 1, q & 1, ixv);
+                    put(T::NPAIR + (q >> 1), q & 1, iyv);
+                    put(2 * T::NPAIR + (q >> 1), q & 1, iv[t]);
                 }
                 p0 = n0; p1 = n1;
             }
-            // chunk c0 occupies bytes [2 c0, 2 c0 + 16) of the I part and [4 c0, 4 c0 + 32) of the D part (c0 is 0 or a multiple of 8)
-            *reinterpret_cast<uint4 *>(slot + 2 * c0) = make_uint4(wI[0], wI[1], wI[2], wI[3]);
-            *reinterpret_cast<uint4 *>(slot + T::TPL_I_BYTES + 4 * c0) = make_uint4(wD[0], wD[1], wD[2], wD[3]);
-            if (CH > 4) *reinterpret_cast<uint4 *>(slot + T::TPL_I_BYTES + 4 * c0 + 16) = make_uint4(wD[4], wD[5], wD[6], wD[7]);
         }
     }
     __syncwarp();
@@ -567,10 +580,10 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
     short2 *der = reinterpret_cast<short2 *>(uni);          // Scharr on the sample grid (setup phase)
     unsigned char *tile = uni + T::DER_BYTES;                // `next` tile (prefetched at level entry)
     unsigned char *raw_buf = tile + T::TILE_BYTES;          // raw[l & 1]: template neighbourhood of level l (prefetched one level ahead)
-    unsigned char *tpl = raw_buf + 2 * T::RAW_BYTES;        // template patch, run-major (this lane's runs: lane + 32 k)
+    unsigned char *tpl = raw_buf + 2 * T::RAW_BYTES;        // template patch (layout: LKT)
 
     // this lane's runs: (row, first column) -- compile-time count, runtime validity
-    int run_y[T::RPL], run_x[T::RPL];
+    int run_y[T::RPL], run_x[T::RPL], run_off[T::RPL];
     bool run_ok[T::RPL];
 #pragma unroll
     for (int k = 0; k < T::RPL; k++) {
@@ -579,6 +592,14 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
         if (!run_ok[k]) r = 0;
         run_y[k] = r / T::RPR;
         run_x[k] = (r - run_y[k] * T::RPR) * RUN;
+        run_off[k] = run_y[k] * T::TWC + run_x[k];
+    }
+    // half-word masks of the gradient words: zero for runs that do not exist
+    uint32_t wmask[T::NPAIR];
+#pragma unroll
+    for (int i = 0; i < T::NPAIR; i++) {
+        const int k0 = (2 * i) / RUN, k1 = (2 * i + 1) / RUN;
+        wmask[i] = (run_ok[k0] ? 0xffffu : 0u) | ((2 * i + 1 < T::NPX && run_ok[k1]) ? 0xffff0000u : 0u);
     }
 
     const long long pidx = (long long)b * max_pts + pt;
@@ -645,7 +666,9 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
         const int ro = ial4 ? (ipx - 1) - (((ipx - 1) >> 2) << 2) : 0;
         cp_async_wait<2>();
         __syncwarp();
-        int a11 = 0, a12 = 0, a22 = 0;
+        // lane partials of the structure tensor and of c = sum I~ * (Ix~, Iy~): the mismatch vector of an iteration is
+        // b = sum J~ * (Ix~, Iy~) - c, so a sweep never touches I~
+        int a11 = 0, a12 = 0, a22 = 0, c1 = 0, c2 = 0;
         const bool inside = ipx >= 0 && ipy >= 0 && ipx + WW < W && ipy + WH < H;      // every derivative sample is in the level
         if (inside) {
             // 2a. Bilinear interpolation and the Scharr operator are both linear and cv2 rounds only once, after the
@@ -662,18 +685,16 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
             }
             __syncwarp();
             // 3a. template from U: window pixel (x, y) is U(x+1, y+1); its 3x3 Scharr support is U(x..x+2, y..y+2).
-            //     Packed to int16 and stored run-major in shared memory; lanes whose run does not exist store zeros
-            //     (their products then vanish in every sum, no per-pixel predicate anywhere).
+            //     Packed to int16 pairs (layout: LKT); lanes whose run does not exist store zero gradients (their products
+            //     then vanish in every sum, no per-pixel predicate anywhere).
+            uint32_t tw[T::NCH_ALL * 4];
+#pragma unroll
+            for (int i = 0; i < T::NCH_ALL * 4; i++) tw[i] = 0u;
             constexpr int CH = RUN <= 8 ? RUN : 8;
 #pragma unroll
             for (int k = 0; k < T::RPL; k++) {
                 const int *u0 = U + run_y[k] * T::UP + run_x[k], *u1 = u0 + T::UP, *u2 = u1 + T::UP;
-                uint32_t wI[T::TPL_I_BYTES / 4], wD[T::TPL_D_BYTES / 4];
-#pragma unroll
-                for (int i = 0; i < T::TPL_I_BYTES / 4; i++) wI[i] = 0;
-#pragma unroll
-                for (int i = 0; i < T::TPL_D_BYTES / 4; i++) wD[i] = 0;
-                int s11 = 0, s12 = 0, s22 = 0;
+                int s11 = 0, s12 = 0, s22 = 0, t1 = 0, t2 = 0;
 #pragma unroll
                 for (int c0 = 0; c0 < RUN; c0 += CH) {
                     // column terms first: V = [3 10 3] down the three rows, Dv = bottom - top; then Ix = V(x+2) - V(x) and
@@ -688,43 +709,51 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
 #pragma unroll
                     for (int i = 0; i < CH; i++) {
                         if (c0 + i < RUN) {
-                            const int t = c0 + i;
+                            const int q = k * RUN + c0 + i;
                             const int ixv = (V[i + 2] - V[i] + (1 << 13)) >> 14;
                             const int iyv = (3 * (Dv[i] + Dv[i + 2]) + 10 * Dv[i + 1] + (1 << 13)) >> 14;
                             const int iv = (ctr[i + 1] + (1 << 8)) >> 9;
-                            if (t & 1) wI[t / 2] |= (uint32_t)iv << 16; else wI[t / 2] = (uint32_t)iv;
-                            wD[t] = ((uint32_t)ixv & 0xffffu) | ((uint32_t)iyv << 16);
+                            if (q & 1) {
+                                tw[q >> 1] |= (uint32_t)ixv << 16;
+                                tw[T::NPAIR + (q >> 1)] |= (uint32_t)iyv << 16;
+                                tw[2 * T::NPAIR + (q >> 1)] |= (uint32_t)iv << 16;
+                            } else {
+                                tw[q >> 1] = (uint32_t)ixv & 0xffffu;
+                                tw[T::NPAIR + (q >> 1)] = (uint32_t)iyv & 0xffffu;
+                                tw[2 * T::NPAIR + (q >> 1)] = (uint32_t)iv;
+                            }
                             s11 += ixv * ixv; s12 += ixv * iyv; s22 += iyv * iyv;
+                            t1 += iv * ixv; t2 += iv * iyv;
                         }
                     }
                 }
-                const uint32_t okm = run_ok[k] ? 0xffffffffu : 0u;
-                uint4 *slot = reinterpret_cast<uint4 *>(tpl + (lane + 32 * k) * T::TPL_RUN_BYTES);
-#pragma unroll
-                for (int i = 0; i < T::TPL_I_BYTES / 16; i++)
-                    slot[i] = make_uint4(wI[4 * i] & okm, wI[4 * i + 1] & okm, wI[4 * i + 2] & okm, wI[4 * i + 3] & okm);
-#pragma unroll
-                for (int i = 0; i < T::TPL_D_BYTES / 16; i++)
-                    slot[T::TPL_I_BYTES / 16 + i] = make_uint4(wD[4 * i] & okm, wD[4 * i + 1] & okm, wD[4 * i + 2] & okm, wD[4 * i + 3] & okm);
-                if (run_ok[k]) { a11 += s11; a12 += s12; a22 += s22; }
+                if (run_ok[k]) { a11 += s11; a12 += s12; a22 += s22; c1 += t1; c2 += t2; }
             }
+#pragma unroll
+            for (int i = 0; i < T::NW_D; i++) tw[i] &= wmask[i < T::NPAIR ? i : i - T::NPAIR];
+            uint4 *slot = reinterpret_cast<uint4 *>(tpl) + lane;
+#pragma unroll
+            for (int c = 0; c < T::NCH_ALL; c++) slot[c * 32] = make_uint4(tw[4 * c], tw[4 * c + 1], tw[4 * c + 2], tw[4 * c + 3]);
         } else {
             // 2b/3b. window touches the border of the level (cold): derivative samples outside the level are ZERO (cv2's
             //        zero-bordered derivative image) while image samples are mirrored, so the linearity shortcut does not
-            //        hold; a rolled, non-inlined routine writes the template (run-major) and the lanes re-read their runs.
+            //        hold; a rolled, non-inlined routine writes the template and the lanes re-read their words.
             for (int i = lane; i < T::TPL_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(tpl)[i] = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
             template_border<T>(raw, ro, der, tpl, ipx, ipy, W, H, w00, w01, w10, w11, lane);
+            const uint32_t *mine = reinterpret_cast<const uint32_t *>(tpl + lane * 16);
+#pragma unroll 1
+            for (int i = 0; i < T::NPAIR; i++) {
+                const uint32_t wx = mine[(i >> 2) * 128 + (i & 3)], wy = mine[((T::NPAIR + i) >> 2) * 128 + ((T::NPAIR + i) & 3)],
+                               wi = mine[((2 * T::NPAIR + i) >> 2) * 128 + ((2 * T::NPAIR + i) & 3)];
 #pragma unroll
-            for (int k = 0; k < T::RPL; k++) {
-                const short2 *d = reinterpret_cast<const short2 *>(tpl + (lane + 32 * k) * T::TPL_RUN_BYTES + T::TPL_I_BYTES);
-#pragma unroll
-                for (int t = 0; t < RUN; t++) {
-                    const short2 e = d[t];
-                    a11 += e.x * e.x; a12 += e.x * e.y; a22 += e.y * e.y;
+                for (int h = 0; h < 2; h++) {
+                    const int ixv = (int)(short)(wx >> (16 * h)), iyv = (int)(short)(wy >> (16 * h)), iv = (int)((wi >> (16 * h)) & 0xffffu);
+                    a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv; c1 += iv * ixv; c2 += iv * iyv;
                 }
             }
         }
+        const long long sc1 = warp_sum(c1), sc2 = warp_sum(c2);
         const float A11 = __fmul_rn((float)warp_sum(a11), FLT_SCALE);
         const float A12 = __fmul_rn((float)warp_sum(a12), FLT_SCALE);
         const float A22 = __fmul_rn((float)warp_sum(a22), FLT_SCALE);
@@ -744,8 +773,12 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
         tile_pending = false;
         __syncwarp();
 
-        // samples `next` at (ix,iy) through the smem tile; f(k, t, J - I) for every owned window pixel
-        auto sweep = [&](int ix, int iy, auto f) {
+        // One sweep of the window at integer origin (ix, iy) of `next` (through the smem tile) with the current weights.
+        // SweepB: o0..o3 = warp sums of J~ * Ix~ and J~ * Iy~, each split by the byte of J~ (J~ is a 13-bit value: the two
+        // bytes of two neighbouring pixels are packed by one PRMT and multiplied with the int16 gradient pairs by DP2A;
+        // low-byte and high-byte sums fit one REDUX each, sum = o_lo + 256 * o_hi).  SweepErr: o0 = warp sum of |J~ - I~|.
+        auto sweep = [&](int ix, int iy, auto mode, int &o0, int &o1, int &o2, int &o3) {
+            constexpr bool ERR = decltype(mode)::value;
             int ox = ix - tx0, oy = iy - ty0;
             if (ox < 0 || oy < 0 || ox + WW + 1 > T::TWC || oy + WH + 1 > T::TH) {
                 __syncwarp();
@@ -757,28 +790,49 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
                 ox = ix - tx0; oy = iy - ty0;
             }
             const int wT = (w00 & 0xffff) | (w01 << 16), wB = (w10 & 0xffff) | (w11 << 16);
+            const int toff = oy * T::TWC + ox;
+            const uint4 *slot = reinterpret_cast<const uint4 *>(tpl) + lane;
+            int v[T::NPX + 1];
+            v[T::NPX] = 0;
 #pragma unroll
             for (int k = 0; k < T::RPL; k++) {
-                const unsigned char *r0 = tile + (oy + run_y[k]) * T::TWC;
-                int v[RUN];
-                bilinear_run<RUN>(r0, r0 + T::TWC, ox + run_x[k], wT, wB, v);
-                const uint4 *slot = reinterpret_cast<const uint4 *>(tpl + (lane + 32 * k) * T::TPL_RUN_BYTES);
-                uint32_t wI[T::TPL_I_BYTES / 4], wD[T::TPL_D_BYTES / 4];
+                int vv[RUN];
+                bilinear_run<RUN>(tile, tile + T::TWC, toff + run_off[k], wT, wB, vv);
 #pragma unroll
-                for (int i = 0; i < T::TPL_I_BYTES / 16; i++) {
-                    const uint4 q = slot[i];
-                    wI[4 * i] = q.x; wI[4 * i + 1] = q.y; wI[4 * i + 2] = q.z; wI[4 * i + 3] = q.w;
-                }
+                for (int t = 0; t < RUN; t++) v[k * RUN + t] = vv[t];
+            }
+            if constexpr (!ERR) {
+                uint32_t tw[T::NCH_D * 4];
 #pragma unroll
-                for (int i = 0; i < T::TPL_D_BYTES / 16; i++) {
-                    const uint4 q = slot[T::TPL_I_BYTES / 16 + i];
-                    wD[4 * i] = q.x; wD[4 * i + 1] = q.y; wD[4 * i + 2] = q.z; wD[4 * i + 3] = q.w;
+                for (int c = 0; c < T::NCH_D; c++) {
+                    const uint4 q = slot[c * 32];
+                    tw[4 * c] = q.x; tw[4 * c + 1] = q.y; tw[4 * c + 2] = q.z; tw[4 * c + 3] = q.w;
                 }
+                int xl = 0, xh = 0, yl = 0, yh = 0;
 #pragma unroll
-                for (int t = 0; t < RUN; t++) {
-                    const int iv = (t & 1) ? (int)(wI[t / 2] >> 16) : (int)(wI[t / 2] & 0xffffu);
-                    f(k, v[t] - iv, wD[t]);
+                for (int i = 0; i < T::NPAIR; i++) {
+                    const uint32_t jj = prmt((uint32_t)v[2 * i], (uint32_t)v[2 * i + 1], 0x5140u);   // bytes (lo0, lo1, hi0, hi1)
+                    xl = dp2a_lo((int)tw[i], jj, xl); xh = dp2a_hi((int)tw[i], jj, xh);
+                    yl = dp2a_lo((int)tw[T::NPAIR + i], jj, yl); yh = dp2a_hi((int)tw[T::NPAIR + i], jj, yh);
                 }
+                o0 = __reduce_add_sync(0xffffffffu, xl); o1 = __reduce_add_sync(0xffffffffu, xh);
+                o2 = __reduce_add_sync(0xffffffffu, yl); o3 = __reduce_add_sync(0xffffffffu, yh);
+            } else {
+                constexpr int C0 = (2 * T::NPAIR) / 4, C1 = (3 * T::NPAIR + 3) / 4;      // chunks holding the I~ words
+                uint32_t tw[(C1 - C0) * 4];
+#pragma unroll
+                for (int c = C0; c < C1; c++) {
+                    const uint4 q = slot[c * 32];
+                    tw[4 * (c - C0)] = q.x; tw[4 * (c - C0) + 1] = q.y; tw[4 * (c - C0) + 2] = q.z; tw[4 * (c - C0) + 3] = q.w;
+                }
+                int se = 0;
+#pragma unroll
+                for (int q = 0; q < T::NPX; q++) {
+                    const uint32_t w = tw[2 * T::NPAIR + (q >> 1) - 4 * C0];
+                    const int iv = (q & 1) ? (int)(w >> 16) : (int)(w & 0xffffu);
+                    se += run_ok[q / RUN] ? abs(v[q] - iv) : 0;
+                }
+                o0 = __reduce_add_sync(0xffffffffu, se);
             }
         };
 
@@ -789,12 +843,13 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
                 break;
             }
             weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
-            int b1 = 0, b2 = 0;
+            int s0, s1, s2, s3;
             // (runs that do not exist hold a zero template: their terms vanish)
-            sweep(inx, iny, [&](int, int diff, uint32_t d) { b1 += diff * (int)(short)(d & 0xffffu); b2 += diff * ((int)d >> 16); });
+            sweep(inx, iny, SweepB{}, s0, s1, s2, s3);
             iters++;
-            const float fb1 = __fmul_rn((float)warp_sum(b1), FLT_SCALE);
-            const float fb2 = __fmul_rn((float)warp_sum(b2), FLT_SCALE);
+            const long long b1 = (long long)s0 + ((long long)s1 << 8) - sc1, b2 = (long long)s2 + ((long long)s3 << 8) - sc2;
+            const float fb1 = __fmul_rn((float)b1, FLT_SCALE);
+            const float fb2 = __fmul_rn((float)b2, FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
@@ -812,9 +867,9 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
             const int iex = __float2int_rd(ex), iey = __float2int_rd(ey);
             if (out_of_level(ex, ey, iex, iey, WW, WH, W, H)) { st = false; continue; }
             weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
-            int se = 0;
-            sweep(iex, iey, [&](int k, int diff, uint32_t) { se += run_ok[k] ? abs(diff) : 0; });
-            ev = __fdiv_rn((float)warp_sum(se), (float)(32 * WW * WH));
+            int se, u1, u2, u3;
+            sweep(iex, iey, SweepErr{}, se, u1, u2, u3);
+            ev = __fdiv_rn((float)se, (float)(32 * WW * WH));
         }
     }
     if (lane == 0) {
@@ -833,12 +888,10 @@ int launch_lk_t(const LKLevels &lv, int n_levels, int max_count, double eps, con
 {
     using T = LKT<WW, WH, RUN, MARGIN, DWP_, TWC_>;
     constexpr size_t smem = (size_t)T::PER_WARP * LKT_WARPS;
-    static bool attr_set = false;
-    if (!attr_set) {
+    LKF_FUNC_ATTRS({
         LKF_CUDA(cudaFuncSetAttribute(k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LKF_CUDA(cudaFuncSetAttribute(k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
-    }
+    });
     dim3 grid((max_pts + LKT_WARPS - 1) / LKT_WARPS, B);
     k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB><<<grid, LKT_WARPS * 32, smem, s>>>(
         lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, prev_pts, pt_counts, max_pts, next_pts, status, err, iters,
@@ -1148,7 +1201,7 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     }
     int rc = 1;
     if (p->win_w == 21 && p->win_h == 21)
-        rc = launch_lk_t<21, 21, 7, 1, 22, 28, 24>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<21, 21, 7, 1, 22, 28, 28>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 15 && p->win_h == 15)
         rc = launch_lk_t<15, 15, 5, 1, 17, 24, 24>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 31 && p->win_h == 31)
@@ -1162,12 +1215,12 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     if (rc < 0) return rc;
     if (rc == LKF_OK) { LKF_LAUNCH_CHECK(ctx); return LKF_OK; }
     if (area <= 2048) {      // int32 lane partials cannot overflow (<= 64 px/lane * 8160*4080)
-        if (smem > 48 * 1024) LKF_CUDA(cudaFuncSetAttribute(k_lk_track<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LKF_FUNC_ATTRS(LKF_CUDA(cudaFuncSetAttribute(k_lk_track<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
         k_lk_track<int><<<grid, LK_WARPS * 32, smem, s>>>(lv, n_levels, p->win_w, p->win_h, max_count, make_eps(eps), p->flags,
                                                           p->min_eig_threshold, prev_pts, pt_counts, max_pts, next_pts,
                                                           status, err, iters, (int)pw);
     } else {
-        if (smem > 48 * 1024) LKF_CUDA(cudaFuncSetAttribute(k_lk_track<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LKF_FUNC_ATTRS(LKF_CUDA(cudaFuncSetAttribute(k_lk_track<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
         k_lk_track<long long><<<grid, LK_WARPS * 32, smem, s>>>(lv, n_levels, p->win_w, p->win_h, max_count, make_eps(eps), p->flags,
                                                                 p->min_eig_threshold, prev_pts, pt_counts, max_pts,
                                                                 next_pts, status, err, iters, (int)pw);

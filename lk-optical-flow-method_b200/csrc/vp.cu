@@ -372,7 +372,7 @@ LKF_EXPORT int lkf_vp_frame(const lkf_vp_params *P, lkf_vp_state *states, int n_
     size_t smem = (size_t)2 * maxp * sizeof(LineRec) + (size_t)8 * maxp * sizeof(float) + (size_t)maxp * sizeof(double) +
                   (size_t)(maxp + 1) * sizeof(int) + (size_t)VP_NT * sizeof(CpRec) + 64;
     if (smem > 200 * 1024) return LKF_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024) LKF_CUDA(cudaFuncSetAttribute(k_vp_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LKF_FUNC_ATTRS(LKF_CUDA(cudaFuncSetAttribute(k_vp_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
     k_vp_frame<<<n_clips, VP_NT, smem, (cudaStream_t)stream>>>(*P, states, p0, p1, status, counts, maxp,
                                                                (const uint8_t *)roi_mask->data, roi_mask->row_pitch,
                                                                roi_mask->height, roi_mask->width, rows, row_capacity, refresh_out,
