@@ -19,11 +19,26 @@ void lkf_count_launch(lkf_ctx *ctx)
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
-int lkf_scratch(lkf_ctx *ctx, int slot, size_t bytes, void **out)
+// Scratch of a ctx: grow-only.  A ctx serves ONE stream at a time (calls on one ctx are not re-entrant and its scratch is not
+// ordered across streams).  A pointer handed out while `stream` is being captured is baked into the CUDA graph, so that slot
+// is pinned from then on: it is never freed, and a later request that would need it to grow is refused
+// (LKF_ERR_UNSUPPORTED) instead of leaving the graph with a dangling pointer -- size everything with one eager call before
+// capturing, and give every captured pipeline its own ctx.  Growth itself (cudaFree + cudaMalloc) is refused during capture.
+int lkf_scratch(lkf_ctx *ctx, int slot, size_t bytes, void **out, cudaStream_t stream)
 {
     if (!ctx || slot < 0 || slot >= 8) return LKF_ERR_ARG;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (stream) LKF_CUDA(cudaStreamIsCapturing(stream, &cs));
+    const bool capturing = cs != cudaStreamCaptureStatusNone;
     if (ctx->scratch_bytes[slot] < bytes) {
-        // grow-only; growth synchronises (cudaFree), steady state does not
+        if (capturing || ctx->scratch_pinned[slot]) {
+            snprintf(g_last_error, sizeof(g_last_error),
+                     "workspace scratch %d would have to grow from %zu to %zu bytes %s: run the call once eagerly at full size "
+                     "before capturing, and use one lkf_ctx per captured pipeline", slot, ctx->scratch_bytes[slot], bytes,
+                     capturing ? "during stream capture" : "but a captured CUDA graph holds its address");
+            return LKF_ERR_UNSUPPORTED;
+        }
+        // growth synchronises (cudaFree), steady state does not
         if (ctx->scratch[slot]) LKF_CUDA(cudaFree(ctx->scratch[slot]));
         ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
         size_t want = bytes + bytes / 4 + 256;
@@ -31,6 +46,7 @@ int lkf_scratch(lkf_ctx *ctx, int slot, size_t bytes, void **out)
         if (e != cudaSuccess) { lkf_set_error("cudaMalloc(scratch)", e); return LKF_ERR_NOMEM; }
         ctx->scratch_bytes[slot] = want;
     }
+    if (capturing) ctx->scratch_pinned[slot] = true;
     *out = ctx->scratch[slot];
     return LKF_OK;
 }

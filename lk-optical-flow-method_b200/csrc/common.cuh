@@ -14,10 +14,11 @@ struct lkf_ctx {
     // grow-only scratch (GFTT candidates, sort keys, cell grid, per-image scalars)
     void *scratch[8];
     size_t scratch_bytes[8];
+    bool scratch_pinned[8];     // handed out while a stream was capturing: a CUDA graph holds the raw pointer, never freed again
 };
 
 void lkf_set_error(const char *what, cudaError_t e);
-int lkf_scratch(lkf_ctx *ctx, int slot, size_t bytes, void **out);
+int lkf_scratch(lkf_ctx *ctx, int slot, size_t bytes, void **out, cudaStream_t stream);
 
 #define LKF_CUDA(call)                                                   \
     do {                                                                 \

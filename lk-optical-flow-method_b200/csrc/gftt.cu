@@ -860,10 +860,10 @@ static int gftt_prepare(lkf_ctx *ctx, const lkf_gftt_params *p, int B, int H, in
     void *keys, *cnt, *top;
     int rc;
     const size_t cnt_ints = (size_t)g->lists * (2 + GF_BINS);
-    if ((rc = lkf_scratch(ctx, 0, (size_t)g->lists * g->cap * 8, &keys)) != LKF_OK) return rc;
-    if ((rc = lkf_scratch(ctx, 1, cnt_ints * sizeof(int), &cnt)) != LKF_OK) return rc;
-    if ((rc = lkf_scratch(ctx, 2, (size_t)g->lists * g->cap * 5, &g->gaux)) != LKF_OK) return rc;     // next (u32) + state (u8), large lists only
-    if ((rc = lkf_scratch(ctx, 4, (size_t)g->lists * g->cap * 8, &top)) != LKF_OK) return rc;        // strongest candidates of large lists
+    if ((rc = lkf_scratch(ctx, 0, (size_t)g->lists * g->cap * 8, &keys, (cudaStream_t)stream)) != LKF_OK) return rc;
+    if ((rc = lkf_scratch(ctx, 1, cnt_ints * sizeof(int), &cnt, (cudaStream_t)stream)) != LKF_OK) return rc;
+    if ((rc = lkf_scratch(ctx, 2, (size_t)g->lists * g->cap * 5, &g->gaux, (cudaStream_t)stream)) != LKF_OK) return rc;     // next (u32) + state (u8), large lists only
+    if ((rc = lkf_scratch(ctx, 4, (size_t)g->lists * g->cap * 8, &top, (cudaStream_t)stream)) != LKF_OK) return rc;        // strongest candidates of large lists
     g->keys = (unsigned long long *)keys;
     g->top = (unsigned long long *)top;
     g->maxkey = (unsigned *)cnt;
@@ -937,7 +937,7 @@ LKF_EXPORT int lkf_gftt_detect(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf
     if (!ctx || !p || !img_ok(src, 1, 1)) return LKF_ERR_ARG;
     void *eigbuf;
     const size_t pitch = ((size_t)src->width * 4 + 15) & ~(size_t)15;
-    int rc = lkf_scratch(ctx, 3, pitch * src->height * src->batch, &eigbuf);
+    int rc = lkf_scratch(ctx, 3, pitch * src->height * src->batch, &eigbuf, (cudaStream_t)stream);
     if (rc != LKF_OK) return rc;
     lkf_image eig = {eigbuf, src->batch, src->height, src->width, 1, (int64_t)pitch, (int64_t)(pitch * src->height)};
     const int B = src->batch, H = src->height, W = src->width;

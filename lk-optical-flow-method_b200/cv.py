@@ -15,6 +15,15 @@ current stream and CUDA tensors are returned without synchronising.  Anything cv
 scripts never exercise raises `error` instead of mis-computing.  Every other attribute
 (VideoCapture, fillPoly, circle, ...) is forwarded to the real cv2 when it is installed, so an
 unmodified script keeps working; none of those are on the hot path.
+
+Work cache.  The scripts call goodFeaturesToTrack four times on the same image (one ROI mask each,
+VP.py:500-507, 702-711), calcOpticalFlowPyrLK twice on the same frame pair (VP.py:545-546, one point group each) and carry
+`processed_old_frame = processed_frame.copy()` to the next frame (VP.py:682).  Host images are therefore looked up in
+a small content-keyed cache (exact byte comparison against a private copy -- never a hash, so a hit is always the same
+image; an array mutated in place simply misses): a hit reuses the device copy, its pyramid and its min-eigenvalue map, and
+host results that this module returned (the gray / blurred frame) are registered with the device tensor they came from,
+so the next call on them needs no upload.  No signature changes; `cache_clear()` / `cache_stats()` / `cache_enable()` are
+extras.  Callers are single-threaded.
 """
 import numpy as np
 import torch
@@ -33,8 +42,104 @@ BORDER_DEFAULT = 4
 BORDER_REFLECT_101 = 4
 
 
-class error(Exception):
-    """Counterpart of cv2.error for argument checks of the replaced functions."""
+try:                                    # after patch(cv2) a script's `except cv2.error` must still catch our argument errors
+    import cv2 as _cv2
+    _ErrorBase = _cv2.error
+except ImportError:                     # pragma: no cover - cv2 is part of the image
+    _ErrorBase = Exception
+
+
+class error(_ErrorBase):
+    """Counterpart of cv2.error for argument checks of the replaced functions (a subclass of cv2.error when cv2 is
+    importable)."""
+
+
+# ---- content-keyed work cache ---------------------------------------------------------------------------------
+class _Entry:
+    __slots__ = ("host", "sig", "dev", "pyr", "eig")
+
+    def __init__(self, host, sig, dev):
+        self.host, self.sig, self.dev = host, sig, dev
+        self.pyr = {}        # n_levels -> [level tensors]
+        self.eig = {}        # blockSize -> min-eigenvalue map
+
+
+class _ImageCache:
+    """Most-recently-used list of host images with their device-resident products."""
+
+    def __init__(self, capacity):
+        self.capacity = capacity
+        self.items = []
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _sig(a):
+        # a few rows as a cheap first test; the decision is always the full comparison below
+        h = a.shape[0]
+        return a[:: max(1, h // 4)].tobytes()
+
+    def find(self, a):
+        sig = None
+        for i, e in enumerate(self.items):
+            if e.host.shape != a.shape or e.host.dtype != a.dtype:
+                continue
+            if sig is None:
+                sig = self._sig(a)
+            if e.sig == sig and np.array_equal(e.host, a):
+                if i:
+                    self.items.insert(0, self.items.pop(i))
+                self.hits += 1
+                return e
+        self.misses += 1
+        return None
+
+    def add(self, a, dev):
+        e = _Entry(np.array(a, copy=True), self._sig(a), dev)
+        self.items.insert(0, e)
+        del self.items[self.capacity:]
+        return e
+
+
+_cache_on = True
+_images = _ImageCache(6)      # frames: prev, next, the gray intermediate, a few spares
+_masks = _ImageCache(8)       # ROI masks (the scripts use four)
+
+
+def cache_enable(on=True):
+    """Switch the work cache on/off (off = every call uploads and recomputes, like round 1)."""
+    global _cache_on
+    _cache_on = bool(on)
+    cache_clear()
+
+
+def cache_clear():
+    _images.items.clear()
+    _masks.items.clear()
+    _images.hits = _images.misses = _masks.hits = _masks.misses = 0
+
+
+def cache_stats():
+    return dict(image_hits=_images.hits, image_misses=_images.misses, mask_hits=_masks.hits, mask_misses=_masks.misses,
+                images=len(_images.items), masks=len(_masks.items))
+
+
+def _host_image(a, cache=None):
+    """host uint8 image -> cache entry (device copy uploaded on a miss)."""
+    cache = _images if cache is None else cache
+    host = as_host_array(a)
+    if not _cache_on:
+        return _Entry(host, None, _to_dev(host))
+    e = cache.find(host)
+    if e is None or e.dev.device != _dev():
+        e = cache.add(host, _to_dev(host))
+    return e
+
+
+def _register(host_result, dev):
+    """a host array this module is about to return + the device tensor it was copied from."""
+    if _cache_on and isinstance(host_result, np.ndarray):
+        _images.add(host_result, dev)
+    return host_result
 
 
 def _dev():
@@ -79,7 +184,8 @@ def cvtColor(src, code, dst=None, dstCn=0):
     if is_device(src):
         return ops.bgr2gray(src)[0]
     host = as_host_array(src)
-    return _back(ops.bgr2gray(_to_dev(host))[0], src)
+    g = ops.bgr2gray(_to_dev(host))[0]
+    return _register(_back(g, src), g)
 
 
 def GaussianBlur(src, ksize, sigmaX, dst=None, sigmaY=0, borderType=BORDER_DEFAULT):
@@ -89,8 +195,8 @@ def GaussianBlur(src, ksize, sigmaX, dst=None, sigmaY=0, borderType=BORDER_DEFAU
     _check_u8_image(src, "src", 1)
     if is_device(src):
         return ops.gaussian_blur3(src)[0]
-    host = as_host_array(src)
-    return _back(ops.gaussian_blur3(_to_dev(host))[0], src)
+    b = ops.gaussian_blur3(_host_image(src).dev)[0]
+    return _register(_back(b, src), b)
 
 
 def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, corners=None, mask=None, blockSize=3,
@@ -110,14 +216,26 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, corners=No
         if tuple(mask.shape) != (H, W) or mask.dtype not in (np.uint8, torch.uint8):
             raise error("goodFeaturesToTrack: mask must be CV_8UC1 of the image size")
     on_dev = is_device(image)
-    img_d = image if on_dev else _to_dev(as_host_array(image))
-    mask_d = None
-    if mask is not None:
-        mask_d = mask if is_device(mask) else _to_dev(as_host_array(mask))
-    max_out = int(maxCorners) if maxCorners > 0 else max(1, (H * W) // 4)
-    eig = ops.min_eigen(img_d, blockSize)
-    cor, cnt = ops.gftt_select(eig, mask_d, maxCorners, qualityLevel, minDistance, max_out)
-    n = int(cnt[0].item())                     # one sync: the count decides the output shape
+    try:
+        if on_dev:
+            eig = ops.min_eigen(image, blockSize)
+        else:
+            ent = _host_image(image)
+            eig = ent.eig.get(int(blockSize))
+            if eig is None:                                 # one map serves the four masked calls of a refresh
+                eig = ent.eig[int(blockSize)] = ops.min_eigen(ent.dev, blockSize)
+        mask_d = None
+        if mask is not None:
+            mask_d = mask if is_device(mask) else _host_image(mask, _masks).dev
+        max_out = int(maxCorners) if maxCorners > 0 else 4096
+        while True:
+            cor, cnt = ops.gftt_select(eig, mask_d, maxCorners, qualityLevel, minDistance, max_out)
+            n = int(cnt[0].item())                 # one sync: the count decides the output shape
+            if n >= 0 or maxCorners > 0 or max_out >= H * W:
+                break
+            max_out = min(H * W, max_out * 8)      # maxCorners <= 0 means "all corners" (cv2): grow the row and repeat
+    except LkfError as e:
+        raise error(str(e)) from e
     if n < 0:
         raise error("goodFeaturesToTrack: corner capacity exceeded")
     if n == 0:
@@ -169,17 +287,26 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status=None, err=No
             raise error("calcOpticalFlowPyrLK: OPTFLOW_USE_INITIAL_FLOW needs nextPts of the same size")
     H, W = prevImg.shape
     on_dev = is_device(prevPts)
-    prev_d = prevImg if is_device(prevImg) else _to_dev(as_host_array(prevImg))
-    next_d = nextImg if is_device(nextImg) else _to_dev(as_host_array(nextImg))
+    prev_e = None if is_device(prevImg) else _host_image(prevImg)
+    next_e = None if is_device(nextImg) else _host_image(nextImg)
     pts_d = (prevPts if on_dev else _to_dev(as_host_array(prevPts))).reshape(1, n, 2)
     init_d = None
     if flags & OPTFLOW_USE_INITIAL_FLOW:
         init_d = (nextPts if is_device(nextPts) else _to_dev(as_host_array(nextPts))).reshape(1, n, 2)
     n_levels = ops.effective_levels(H, W, winSize, maxLevel)
     params = ops.lk_params_struct(winSize, maxLevel, criteria, flags, minEigThreshold)
+    def pyramid(img, ent):
+        # one pyramid per image: shared by the two point-group calls of a frame and carried next -> prev
+        if ent is None:
+            return ops.build_pyramid(img, n_levels)
+        pyr = ent.pyr.get(n_levels)
+        if pyr is None:
+            pyr = ent.pyr[n_levels] = ops.build_pyramid(ent.dev, n_levels)
+        return pyr
+
     try:
-        ppyr = ops.build_pyramid(prev_d, n_levels)
-        npyr = ops.build_pyramid(next_d, n_levels)
+        ppyr = pyramid(prevImg, prev_e)
+        npyr = pyramid(nextImg, next_e)
         nxt, st, er = ops.pyrlk(ppyr, npyr, pts_d, params, next_pts=init_d)
     except LkfError as e:
         raise error(str(e)) from e

@@ -94,8 +94,22 @@ class Workspace:
         return int(self.lib.lkf_ctx_launch_count(None))
 
     @classmethod
+    def private(cls, device=None):
+        """A workspace of its own (own lkf_ctx, own scratch) for an object that captures CUDA graphs: a graph bakes the
+        scratch addresses in, so they must not be shared with calls that could make the scratch grow (abi.cu: lkf_scratch)."""
+        require_cuda()
+        return cls(torch.cuda.current_device() if device is None else device)
+
+    def use(self):
+        """Context manager: inside it Workspace.current() (and so every ops.* call) is this workspace."""
+        return _Use(self)
+
+    @classmethod
     def current(cls):
         require_cuda()
+        stack = getattr(cls._tls, "stack", None)
+        if stack:
+            return stack[-1]
         dev = torch.cuda.current_device()
         d = getattr(cls._tls, "ws", None)
         if d is None:
@@ -103,6 +117,22 @@ class Workspace:
         if dev not in d:
             d[dev] = cls(dev)
         return d[dev]
+
+
+class _Use:
+    def __init__(self, ws):
+        self.ws = ws
+
+    def __enter__(self):
+        st = getattr(Workspace._tls, "stack", None)
+        if st is None:
+            st = Workspace._tls.stack = []
+        st.append(self.ws)
+        return self.ws
+
+    def __exit__(self, *exc):
+        Workspace._tls.stack.pop()
+        return False
 
 
 def pyramid_shapes(H, W, n_levels):

@@ -21,6 +21,15 @@ from . import ops
 from .device import Workspace, pyramid_shapes
 
 
+def _in_ws(fn):
+    """run a stage method inside the pipeline's own workspace"""
+    def wrapped(self, *a, **k):
+        with self.ws.use():
+            return fn(self, *a, **k)
+    wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+    return wrapped
+
+
 class PairPipeline:
     def __init__(self, B, H, W, n_pts, lk_params=None, gftt_params=None, refresh_every=10, device=None):
         self.B, self.H, self.W, self.N = int(B), int(H), int(W), int(n_pts)
@@ -34,7 +43,7 @@ class PairPipeline:
         self.refresh_every = int(refresh_every)
         self.n_levels = ops.effective_levels(H, W, self.lk["winSize"], self.lk["maxLevel"])
         self.params = ops.lk_params_struct(**self.lk)
-        self.ws = Workspace.current()
+        self.ws = Workspace.private()      # own ctx: the captured step holds this workspace's scratch addresses
         # pyramid slots 0..B : slot 0 = last frame of the previous step
         self.levels = [torch.zeros((self.B + 1, h, w), dtype=torch.uint8, device=self.dev)
                        for (h, w) in pyramid_shapes(H, W, self.n_levels)]
@@ -60,6 +69,7 @@ class PairPipeline:
         self.graph = None
 
     # -- state -----------------------------------------------------------------------------------
+    @_in_ws
     def prime(self, first_bgr):
         """Process the frame preceding the first pair into slot 0 ([H,W,3] uint8 CUDA tensor)."""
         ops.process_img(first_bgr[None] if first_bgr.dim() == 3 else first_bgr, out=self.levels[0][0:1])
@@ -72,16 +82,19 @@ class PairPipeline:
             self.counts.copy_(counts)
 
     # -- stages (each is one kernel launch or a fixed short sequence) -----------------------------
+    @_in_ws
     def stage_process(self, bgr, lo=0, hi=None):
         """process_img of new frames lo..hi-1 (pyramid slots lo+1..hi)."""
         hi = self.B if hi is None else hi
         ops.process_img(bgr[lo:hi], out=self.levels[0][1 + lo:1 + hi])
 
+    @_in_ws
     def stage_pyramid(self, lo=0, hi=None):
         hi = self.B if hi is None else hi
         for l in range(1, self.n_levels):
             ops.pyr_down(self.levels[l - 1][1 + lo:1 + hi], out=self.levels[l][1 + lo:1 + hi])
 
+    @_in_ws
     def stage_refresh(self):
         if not self.R:
             return
@@ -92,6 +105,7 @@ class PairPipeline:
         self.pts[0:self.B:e].copy_(self.corners)
         self.counts[0:self.B:e].copy_(self.ccounts)
 
+    @_in_ws
     def stage_track(self, want_iters=False):
         prev = [lv[0:self.B] for lv in self.levels]
         nxt = [lv[1:self.B + 1] for lv in self.levels]
@@ -104,10 +118,12 @@ class PairPipeline:
         for lv in self.levels:
             lv[0].copy_(lv[self.B])
 
+    @_in_ws
     def stage_process_pyramid(self, bgr):
         """process_img + the whole pyramid of the B new frames in one ABI call."""
         ops.process_pyramid(bgr, [lv[1:] for lv in self.levels])
 
+    @_in_ws
     def stage_track_main(self, lo=0, hi=None):
         """LK of pairs lo..hi-1 that are NOT refreshed in this step (point count 0 for the refreshed ones)."""
         hi = self.B if hi is None else hi
@@ -117,12 +133,14 @@ class PairPipeline:
         ops.pyrlk(prev, nxt, self.pts[lo:hi], self.params, counts=self.counts_main[lo:hi],
                   out=(self.next_pts[lo:hi], self.status[lo:hi], self.err[lo:hi]))
 
+    @_in_ws
     def stage_refresh_detect(self):
         """Corner refresh of every refresh_every-th pair (needs level 0 of the previous frames only)."""
         e = self.refresh_every
         ops.gftt_detect(self.levels[0][0:self.B:e], None, self.gftt["maxCorners"], self.gftt["qualityLevel"],
                         self.gftt["minDistance"], self.gftt["blockSize"], self.N, out=(self.corners, self.ccounts))
 
+    @_in_ws
     def stage_track_refreshed(self):
         """LK launch of exactly the refreshed pairs (strided views of the pyramid slots), results scattered into the
         per-pair outputs."""
@@ -138,6 +156,10 @@ class PairPipeline:
 
     def step(self, bgr):
         """bgr: [B,H,W,3] uint8 CUDA tensor = the B new frames of this step."""
+        with self.ws.use():
+            self._step(bgr)
+
+    def _step(self, bgr):
         if not (self.R and self.overlap):
             self.stage_process_pyramid(bgr)
             self.stage_refresh()

@@ -118,7 +118,7 @@ class ClipBatchRunner:
         self.Hei = int(self.WID * (float(h) / float(w)))                      # VP.py:430-432
         self.resize_needed = (self.Hei, self.WID) != (h, w)
         self.dev = torch.device("cuda", torch.cuda.current_device())
-        self.ws = Workspace.current()
+        self.ws = Workspace.private()      # own ctx: step_graph's graphs hold this workspace's scratch addresses
         B, H, W = self.B, self.Hei, self.WID
         self.fp = feature_params(cfg)
         self.maxc = max(1, self.fp["maxCorners"])
@@ -184,11 +184,16 @@ class ClipBatchRunner:
     # -- the frame loop -----------------------------------------------------------------------------
     def start(self, first_frames):
         """Step 1-2 of Run(): first frame -> corners of the four ROI sub-masks (VP.py:494-507)."""
-        self._prepare(first_frames, self.cur)
-        self._detect(self.cur, None)
-        self._apply_refresh(force=True)
+        with self.ws.use():
+            self._prepare(first_frames, self.cur)
+            self._detect(self.cur, None)
+            self._apply_refresh(force=True)
 
     def _step_launches(self, frames):
+        with self.ws.use():
+            self._step_launches_ws(frames)
+
+    def _step_launches_ws(self, frames):
         old, new = self.cur, self.cur ^ 1
         self._prepare(frames, new)
         ops.pyrlk(self.pyr[old], self.pyr[new], self.p0, self.lk, out=(self.p1, self.st, self.err))
