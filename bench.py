@@ -39,9 +39,30 @@ WORKLOAD = ("C2: 1920x1080 sparse PyrLK, 2000 pts/pair, 3-level pyramid (maxLeve
             "criteria (EPS|COUNT,10,0.03); per pair process_img(BGR)+pyramid+LK; GFTT(2000,q=0.01,d=7,bs=7) "
             "refresh on every 10th pair")
 METRIC = "frame-pairs/s, 1080p PyrLK 2k pts"
-# dram__bytes_read.sum + dram__bytes_write.sum per frame pair, from the committed ncu --set full captures
-NCU_SOURCE = "profiles/r01_captureE_kernels.md (ncu --set full, per step of 64 pairs, divided by 64)"
-NCU_DRAM_BYTES_PER_PAIR = {"lk_track": (162.3e6 + 7.4e6 + 35.4e6 + 0.4e6) / 64, "process_img": (422.5e6 + 113.4e6) / 64}
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")     # written by tools/ncu_traffic.py from an ncu --set full capture
+
+
+def source_digest():
+    """sha256 over the CUDA sources of the library: a traffic figure is only quoted when it was captured on this build."""
+    import hashlib
+    d = os.path.join(ROOT, "lk-optical-flow-method_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def captured_traffic():
+    """{kernel substring: DRAM bytes per 64-pair step} from the committed capture, or {} when the sources changed since."""
+    try:
+        t = json.load(open(TRAFFIC_FILE))
+    except Exception:
+        return {}, None
+    if t.get("source_digest") != source_digest():
+        return {}, f"{os.path.relpath(TRAFFIC_FILE, ROOT)} is stale (captured on source digest {t.get('source_digest')})"
+    return t.get("dram_bytes_per_step", {}), f"{os.path.relpath(TRAFFIC_FILE, ROOT)} ({t.get('how', 'ncu --set full')})"
 
 
 def env_int(name, default):
@@ -132,6 +153,12 @@ def make_inputs(B, seed, device):
             pts[i0 + j, need:] = adv
     torch.cuda.synchronize()
     return frames, pts
+
+
+def bench_config(B):
+    """`config` of the JSON line: the same dict in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "pairs_per_step_per_gpu": int(B), "points_per_pair": NPTS,
+            "l2": f"inputs larger than L2: {int(B)} BGR frames = {int(B) * 3 * W * H / 1e6:.0f} MB per step"}
 
 
 def lk_ops(iters_total, n_points, n_levels, win):
@@ -273,8 +300,10 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 patches + f32 solves", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": WORKLOAD, "pairs_per_step": tot_pairs / max(1, args.steps),
-                       "note": "each step is a bounded sample (fixed wall budget) of the same per-pair work"},
+            "config": bench_config(args.pairs),
+            "reference_step": {"pairs_per_step": tot_pairs / max(1, args.steps),
+                               "note": "each step is a bounded sample (fixed wall budget) of the same per-pair work"},
+            "gpus_used": 0,
             "cpu_baseline": {"value": v, "unit": "frame-pairs/s", "cores": r["cores"], "kind": r["kind"],
                              "sample": f"{tot_pairs} pairs in {tot_s:.1f} s over {args.steps} steps; last step: {r['sample']}",
                              "variants": r["variants"]},
@@ -282,6 +311,209 @@ def run_reference(args):
             "gpu_launches": 0}
     emit(line)
     return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# C5: 64 independent 1080p clips sharded by clip over the ranks, VP CSV per clip
+# ------------------------------------------------------------------------------------------------
+def c5_clip_frames(c, n_frames, texs, dev):
+    import torch
+    from lk_optical_flow_method_b200 import synth
+    rng = np.random.default_rng(c)
+    foe = (0.48 * (1 + rng.uniform(-0.05, 0.05)), 0.60 * (1 + rng.uniform(-0.05, 0.05)))
+    rate = float(rng.uniform(1.010, 1.020))
+    return [synth.zoom_frame(texs[c % len(texs)], W, H, t, rate=rate, foe=foe) for t in range(n_frames)]
+
+
+def c5_prepare(clips, texs, n_frames, dev):
+    """frames of the clips resident in HBM as per-frame batches + a runner whose step graphs are captured (untimed set-up)"""
+    import torch
+    from lk_optical_flow_method_b200 import vp as V
+    per_clip = [c5_clip_frames(c, n_frames, texs, dev) for c in clips]
+    batches = [torch.stack([per_clip[i][t] for i in range(len(clips))]) for t in range(n_frames)]
+    del per_clip
+    r = V.ClipBatchRunner(len(clips), (H, W), variant="VP", expected_frames=4 * n_frames, TP_NUM=60)
+    buf = torch.empty_like(batches[0])
+    r.start(batches[0])
+    for fr in batches[1:3]:                               # one step per ping-pong parity: both graphs captured
+        buf.copy_(fr)
+        r.step_graph(buf)
+    torch.cuda.synchronize()
+    r.reset()
+    return r, buf, batches
+
+
+def c5_run(clips, r, buf, batches):
+    """The clips in lock-step on this GPU: ({clip: rows}, seconds from the first frame to the rows on the host)."""
+    import torch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r.start(batches[0])
+    for fr in batches[1:]:
+        buf.copy_(fr)
+        r.step_graph(buf)
+    rows = r.rows_host()                                  # synchronises, D2H of every clip's rows
+    dt = time.perf_counter() - t0
+    return {c: rows[i] for i, c in enumerate(clips)}, dt
+
+
+def c5_block(args, rank, world, dev):
+    """BASELINE.json config 5: 64 clips of 1920x1080 (-> 860x483 like the scripts), clip c on rank c mod N, every rank runs
+    its clips in lock-step; the per-clip rows are gathered to rank 0 over a gloo group (host gather, no NCCL on the data
+    path) and written as vps/vps_<clip>.csv.  Timed: first frame -> CSV files on disk, max over ranks.  Rank 0 then repeats
+    all 64 clips alone and compares the CSV bytes."""
+    import hashlib
+    import shutil
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from lk_optical_flow_method_b200 import shard, synth
+    n_clips, n_frames = 64, 17
+    texs = [torch.from_numpy(synth.make_texture(W, H, 100 + k)).to(dev) for k in range(4)]
+    mine = shard.assign(n_clips, world, rank)
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
+    runner, buf, batches = c5_prepare(mine, texs, n_frames, dev)
+    out_dir = tempfile.mkdtemp(prefix="lkf_c5_") if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    rows, dev_s = c5_run(mine, runner, buf, batches)
+    merged = shard.gather_to_root(rows, group=host_group) if world > 1 else rows
+    sha = None
+    if rank == 0:
+        paths = shard.write_vp_csvs(merged, [f"clip{c:02d}" for c in range(n_clips)], out_dir)
+        h = hashlib.sha256()
+        for pth in paths:
+            h.update(open(pth, "rb").read())
+        sha = h.hexdigest()
+    if world > 1:
+        dist.barrier()
+    total_s = time.perf_counter() - t0
+    t = torch.tensor([total_s, dev_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = None
+    if rank == 0:
+        total_s, dev_s = float(t[0]), float(t[1])
+        n_rows = int(sum(len(v) for v in merged.values()))
+        res = {"clips": n_clips, "frames_per_clip": n_frames, "ranks": world, "clips_per_rank": len(mine),
+               "clip_frames_per_s": n_clips * n_frames / total_s, "seconds": total_s, "device_seconds_max_rank": dev_s,
+               "csv_rows": n_rows, "csv_sha256": sha, "gather": "gloo gather_object to rank 0 + one CSV per clip (save_csv schema)",
+               "timed": "first frame of every clip -> CSV files written; frames resident in HBM, step graphs captured beforehand; max "
+                        "over ranks (wall clock: it includes the D2H of the rows, the host gather and the file writes)"}
+        if world > 1:
+            del runner, buf, batches
+            allc = list(range(n_clips))
+            ref_rows, _ = c5_run(allc, *c5_prepare(allc, texs, n_frames, dev))
+            d2 = tempfile.mkdtemp(prefix="lkf_c5ref_")
+            h = hashlib.sha256()
+            for pth in shard.write_vp_csvs(ref_rows, [f"clip{c:02d}" for c in range(n_clips)], d2):
+                h.update(open(pth, "rb").read())
+            shutil.rmtree(d2, ignore_errors=True)
+            res["csv_equal_to_1gpu_run"] = h.hexdigest() == sha
+        shutil.rmtree(out_dir, ignore_errors=True)
+    if world > 1:
+        dist.barrier()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-in boundary: per-call latency of the cv2-signature module with HOST arrays, cv2 beside it
+# ------------------------------------------------------------------------------------------------
+def dropin_block(args):
+    import cv2
+    import torch
+    from lk_optical_flow_method_b200 import cv as b200, synth, vp as V
+    out = {}
+
+    def script_loop(mod, frames, masks, fp, lk, n_groups=2):
+        """the scripts' frame loop reduced to its four hot calls (VP.py:404-425, 500-507, 545-553, 682, 700-711)"""
+        tm = {"process_img": [0.0, 0], "goodFeaturesToTrack": [0.0, 0], "calcOpticalFlowPyrLK": [0.0, 0]}
+
+        def timed(key, fn):
+            t0 = time.perf_counter()
+            r = fn()
+            tm[key][0] += time.perf_counter() - t0
+            tm[key][1] += 1
+            return r
+
+        def detect(img):
+            groups = []
+            for j in range(2):
+                p0 = []
+                for i in range(2):
+                    c = timed("goodFeaturesToTrack", lambda: mod.goodFeaturesToTrack(img, mask=masks[j * 2 + i], **fp))
+                    if c is not None:
+                        p0.extend(c)
+                groups.append(np.array(p0, dtype=np.float32).reshape(-1, 1, 2))
+            return groups
+
+        old = timed("process_img", lambda: mod.GaussianBlur(mod.cvtColor(frames[0], cv2.COLOR_BGR2GRAY), (3, 3), 0))
+        groups = detect(old)
+        t_all = time.perf_counter()
+        for k, f in enumerate(frames[1:], 1):
+            new = timed("process_img", lambda: mod.GaussianBlur(mod.cvtColor(f, cv2.COLOR_BGR2GRAY), (3, 3), 0))
+            nxt = []
+            for g in groups:
+                if len(g) == 0:
+                    nxt.append(g)
+                    continue
+                p1, st, err = timed("calcOpticalFlowPyrLK", lambda: mod.calcOpticalFlowPyrLK(old, new, g, None, **lk))
+                nxt.append(np.ascontiguousarray(p1[st.ravel() == 1].reshape(-1, 1, 2)))
+            groups = nxt
+            old = new.copy()
+            if k % 10 == 0:
+                groups = detect(old)
+        wall = time.perf_counter() - t_all
+        res = {k: 1e6 * v[0] / max(1, v[1]) for k, v in tm.items()}
+        res["frame_ms"] = 1e3 * wall / (len(frames) - 1)
+        return res
+
+    cv2.setNumThreads(os.cpu_count() or 1)
+    for tag, (w, h, n, fp, lk) in {
+            "script_860x483": (860, 483, 41, dict(maxCorners=5, qualityLevel=0.3, minDistance=7, blockSize=7),
+                               dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.03))),
+            "c2_1920x1080": (W, H, 21, dict(maxCorners=500, qualityLevel=0.01, minDistance=7, blockSize=7), LK)}.items():
+        tex = synth.make_texture(w, h, 11)
+        frames = [synth.zoom_frame(tex, w, h, t) for t in range(n)]
+        _, masks = V.roi_masks(w, h)
+        r = {"us_per_call": {}, "points": f"{fp['maxCorners']} corners per ROI mask, 2 point groups"}
+        r["us_per_call"]["cv2"] = script_loop(cv2, frames, masks, fp, lk)
+        b200.cache_enable(True)
+        script_loop(b200, frames[:3], masks, fp, lk)                 # warm-up (workspace, kernel loading)
+        b200.cache_enable(False)
+        r["us_per_call"]["b200_uncached"] = script_loop(b200, frames, masks, fp, lk)
+        b200.cache_enable(True)
+        r["us_per_call"]["b200_cached"] = script_loop(b200, frames, masks, fp, lk)
+        r["cache"] = b200.cache_stats()
+        out[tag] = r
+    # wall time of the unmodified script with and without patch(cv2) (staged copy under baseline/_ref, see tests)
+    script = os.path.join(ROOT, "baseline", "_ref", "VP_detection_using_optical_flow.py")
+    if os.path.exists(script):
+        import shutil
+        import tempfile
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import run_script_headless as R
+        d = tempfile.mkdtemp(prefix="lkf_dropin_")
+        tex = synth.make_texture(1280, 720, 0)
+        for t in range(60):
+            cv2.imwrite(os.path.join(d, f"f_{t:04d}.png"), synth.zoom_frame(tex, 1280, 720, t))
+        res = {}
+        for arm in ("cv2", "patched", "patched"):
+            saved = b200.patch(cv2) if arm == "patched" else None
+            b200.cache_clear()
+            t0 = time.perf_counter()
+            try:
+                text = R.run(script, "f_%04d.png", d)
+            finally:
+                if saved:
+                    b200.unpatch(cv2, saved)
+            res[arm] = {"seconds": time.perf_counter() - t0, "csv_rows": text.count("\n") - 1}
+        shutil.rmtree(d, ignore_errors=True)
+        out["unmodified_VP_script_60_frames_1280x720"] = res
+        out["note"] = ("the script's wall time is dominated by PNG decode, imutils.resize and Python glue (out of the path, SURVEY 2); "
+                       "per-call numbers are the path")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -377,6 +609,23 @@ def run_b200(args):
     ms_total = float(t.item())
     value = world * B * K / (ms_total * 1e-3)
 
+    # ---- sustained leg: >= args.sustain_seconds of back-to-back replays (the K-step region above is a burst of ~20 ms) ---
+    n_sus = max(K, int(np.ceil(args.sustain_seconds * 1e3 / (ms_total / K))))
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(n_sus):
+        replay()
+    s1.record()
+    barrier()
+    t = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sus_ms = float(t.item())
+    sustained = {"value": world * B * n_sus / (sus_ms * 1e-3), "unit": "frame-pairs/s", "steps": int(n_sus),
+                 "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus,
+                 "note": "same graph replayed back to back for seconds; clocks of the whole run in `clocks`"}
+
     # ---- e2e: host buffers, copies inside the timed region ---------------------------------------
     host_frames = new_frames.cpu().pin_memory()
     host_pts = pts.cpu().pin_memory()
@@ -394,7 +643,27 @@ def run_b200(args):
     e2e_value = world * B * K / float(t.item())
     h2d = host_frames.numel() + host_pts.numel() * 4
     d2h = sum(o.numel() * o.element_size() for o in outs[-1])
+    # ---- plain pinned host -> device copy rate at this N (all ranks at once): the ceiling of the e2e figure ----------
+    dst = torch.empty_like(new_frames)
+    dst.copy_(host_frames, non_blocking=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(4):
+        dst.copy_(host_frames, non_blocking=True)
+    c1.record()
+    barrier()
+    t = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gbs = world * 4 * host_frames.numel() / (float(t.item()) * 1e-3) / 1e9
+    h2d_bw = {"GBps_all_ranks": gbs, "GBps_per_rank": gbs / world, "bytes": int(host_frames.numel()),
+              "e2e_h2d_GBps": e2e_value * (h2d / B) / 1e9,
+              "note": "cudaMemcpyAsync of one step's pinned BGR frames, 4 in a row, every rank at the same time"}
+    del dst
     clk = clocks.stop() if rank == 0 else None
+    c5 = c5_block(args, rank, world, dev) if not args.no_c5 else None
+    dropin = dropin_block(args) if (rank == 0 and world == 1 and not args.no_dropin) else None
 
     # ---- per-stage device times: each stage captured in its own CUDA graph and replayed back to back (no launch
     #      gaps inside the timed region), CUDA events on the launch stream --------------------------------------
@@ -464,21 +733,30 @@ def run_b200(args):
     lk_tflops = ops_lk / (lk_ms * 1e-3) / 1e12
     stages["lk_track"].update({"bound": "fp32", "algorithmic_ops": ops_lk, "iterations_per_point": iters_total / max(1, n_tracked),
                                "achieved_TFLOPs": lk_tflops, "frac_of_fp32_peak": lk_tflops / fp32_peak})
+    traffic, traffic_src = captured_traffic()
+
+    def step_traffic(key):
+        v = traffic.get(key)
+        return None if v is None else float(v) * B / 64.0
+
+    sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+    fp32_nominal = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
     dom = stage_names[int(np.argmax(st_ms[:n_step_stages]))]
     if dom == "lk_track":
         roof = {"kernel": "k_lk_track_t<21,21>", "bound": "fp32", "achieved": lk_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": lk_tflops / fp32_peak,
-                "traffic": NCU_DRAM_BYTES_PER_PAIR["lk_track"] * B if B else None,
-                "traffic_source": NCU_SOURCE,
-                "peak_source": "measured in this run (FFMA probe kernel, non-tensor FP32 pipe)",
-                "note": "ALU-bound gather/iterate kernel; ops from the SURVEY 8d model with on-device iteration counts"}
+                "frac": lk_tflops / fp32_peak, "peak_nominal": fp32_nominal, "frac_of_nominal": lk_tflops / fp32_nominal,
+                "traffic": step_traffic("k_lk_track_t"), "traffic_source": traffic_src,
+                "peak_source": "measured in this run (FFMA probe: 16 chains x 128 FFMA per loop trip, non-tensor FP32 pipe); "
+                               "peak_nominal = SMs x 128 lanes x 2 x the SM clock sampled under load",
+                "note": "integer gather/iterate kernel (IMAD/IDP.2A and integer-ALU datapaths run at half the FFMA rate: "
+                        "tools/probe_pipes.py); ops from the SURVEY 8d model with on-device iteration counts"}
     else:
         s_ = stages[dom]
         roof = {"kernel": dom, "bound": "hbm", "achieved": s_["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": s_["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src}
     roof_hbm = {"kernel": "k_blur3_stream<RowBGR> (process_img)", "bound": "hbm", "achieved": stages["process_img"]["achieved_GBps"],
                 "peak": hbm_peak, "unit": "GB/s", "frac": stages["process_img"]["frac_of_hbm_peak"],
-                "traffic": NCU_DRAM_BYTES_PER_PAIR["process_img"] * B, "traffic_source": NCU_SOURCE, "peak_source": peak_src}
+                "traffic": step_traffic("k_blur3_stream"), "traffic_source": traffic_src, "peak_source": peak_src}
 
     line = None
     if rank == 0:
@@ -490,16 +768,17 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8/int32 patches + f32 solves", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "points_per_pair": NPTS,
-                           "l2": f"inputs larger than L2: {B} BGR frames = {B * 3 * P / 1e6:.0f} MB per step",
-                           "timed": "CUDA-graph replay of the whole step, CUDA events on the launch stream"},
+                "config": bench_config(B),
+                "timed": "CUDA-graph replay of the whole step, CUDA events on the launch stream; torch.distributed (NCCL) only for "
+                         "the barrier and the MAX of the timing, never on the data path",
+                "sustained": sustained, "h2d_pinned": h2d_bw, "dropin": dropin, "c5": c5,
                 "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),
                         "note": "pinned host BGR frames + points -> H2D -> kernels -> D2H tracks, double-buffered copy stream",
                         "cpu_binding_rank0": numa},
                 "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
                 "roofline": roof, "roofline_hbm_stencil": roof_hbm, "stages": stages,
-                "fp32_peak_tflops_measured": fp32_peak, "cpu_baseline": cpu, "clocks": clk}
+                "fp32_peak_tflops_measured": fp32_peak, "fp32_peak_tflops_nominal": fp32_nominal, "cpu_baseline": cpu, "clocks": clk}
         emit(line)
     if world > 1:
         dist.barrier()
@@ -535,10 +814,21 @@ def main():
     ap.add_argument("--pairs", type=int, default=64, help="frame pairs per step per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sustain-seconds", type=float, default=3.0, help="length of the sustained leg (graph replays)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 block (64 clips sharded over the ranks, CSV output)")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the per-call drop-in latencies (N=1 only)")
     ap.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_worker:
         return cpu_worker(args.cpu_worker, args.cpu_seconds)
+    if args.impl == "b200" and args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` on its own: start the N ranks the way the driver does
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr",
+               "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if args.impl == "b200" and env_int("WORLD_SIZE", 1) != args.gpus:
+        sys.stderr.write(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={env_int('WORLD_SIZE', 1)}; reporting the ranks that exist\n")
     _quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)

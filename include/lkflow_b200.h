@@ -157,7 +157,7 @@ typedef struct lkf_vp_params {
     int32_t hide_vp_thold;             /* HIDE_VP_THOLD = 50                    (VP.py:644)          */
     int32_t reset_avg_on_hide;         /* 1: VP.py:647, 0: LK_Final.py                               */
     int32_t tp_update_time;            /* TP_UPDATE_TIME = 10                   (VP.py:700)          */
-    int32_t vl_ref;                    /* VP_REF = 300: history rows of the vanishing-line fits (VP.py:52, 654); 0 = no VL */
+    int32_t vl_ref;                    /* VP_REF = 300: history rows of the vanishing-line fits (VP.py:52, 654); 0 = the whole history (Python's all_vp[-0:]); < 0 = no VL */
 } lkf_vp_params;
 
 typedef struct lkf_vp_state {          /* one per clip, device resident, zero-initialised except avg_len */

@@ -130,7 +130,7 @@ def check(status, where):
     if status < 0:
         lib = load()
         msg = lib.lkf_strerror(status).decode()
-        if status == -2:
+        if status in (-2, -3) and lib.lkf_last_error():
             msg += ": " + lib.lkf_last_error().decode()
         raise LkfError(status, where, msg)
     return status

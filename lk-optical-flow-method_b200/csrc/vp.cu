@@ -272,7 +272,7 @@ k_vp_frame(lkf_vp_params P, lkf_vp_state *__restrict__ states, float *__restrict
             } else {
                 if (S.n_rows < row_cap) { rows[2 * S.n_rows] = S.vp_x; rows[2 * S.n_rows + 1] = S.vp_y; S.n_rows++; }
                 else S.row_overflow = 1;
-                s_do_vl = S.vp_moved && P.vl_ref > 0 && !S.row_overflow;      // vl.update(all_vp[-VP_REF:], vp), VP.py:654
+                s_do_vl = S.vp_moved && P.vl_ref >= 0 && !S.row_overflow;     // vl.update(all_vp[-VP_REF:], vp), VP.py:654
             }
         }
     }
@@ -280,7 +280,7 @@ k_vp_frame(lkf_vp_params P, lkf_vp_state *__restrict__ states, float *__restrict
     if (s_do_vl) {
         // VL.update (VP.py:224-245): scipy.stats.linregress slope = (dx.dy / n) / (dx.dx / n) on the de-meaned samples,
         // intercept = ymean - slope * xmean, for y(x) and for x(y); sums by the CTA (float64, fixed order -> deterministic)
-        const int n = min(S.n_rows, P.vl_ref);
+        const int n = P.vl_ref > 0 ? min(S.n_rows, P.vl_ref) : S.n_rows;      // VP_REF = 0: all_vp[-0:] is the whole history
         const double *h = rows + 2 * (size_t)(S.n_rows - n);
         const int lane = tid & 31, wid = tid >> 5;
         auto block_sums = [&](double *v, int cnt) {                       // v[0..cnt) -> s_red[q][0] holds the CTA sums
@@ -343,7 +343,16 @@ __global__ void k_apply_refresh(lkf_vp_state *__restrict__ states, const float *
 {
     const int b = blockIdx.x;
     if (!force && !states[b].refresh) return;
-    const int c[4] = {max(ccounts[4 * b], 0), max(ccounts[4 * b + 1], 0), max(ccounts[4 * b + 2], 0), max(ccounts[4 * b + 3], 0)};
+    // a negative count (-1 - n) reports a capacity overflow of the corner selection: keep the n corners that were written and
+    // flag the clip (bit 1 of row_overflow; the host raises when it reads the rows)
+    int c[4];
+    bool over = false;
+    for (int i = 0; i < 4; i++) {
+        const int v = ccounts[4 * b + i];
+        over |= v < 0;
+        c[i] = v < 0 ? -1 - v : v;
+    }
+    if (over && threadIdx.x == 0) states[b].row_overflow |= 2;
     const int n0 = min(c[0] + c[1], maxp), n1 = min(c[2] + c[3], maxp);
     if (!force && (n0 == 0 || n1 == 0)) return;
     for (int g = 0; g < 2; g++) {

@@ -23,7 +23,11 @@ a small content-keyed cache (exact byte comparison against a private copy -- nev
 image; an array mutated in place simply misses): a hit reuses the device copy, its pyramid and its min-eigenvalue map, and
 host results that this module returned (the gray / blurred frame) are registered with the device tensor they came from,
 so the next call on them needs no upload.  No signature changes; `cache_clear()` / `cache_stats()` / `cache_enable()` are
-extras.  Callers are single-threaded.
+extras.  Callers are single-threaded.  The cache is OFF by default: it removes 1 of 4 eig passes' siblings and 3
+of 4 pyramid builds per script frame (tests/test_gpu_dropin_scripts.py counts the launches), but on a B200 those kernels
+take 5-20 us while the exact host-side comparison costs 30 us (860x483) to 150 us (1080p) per lookup -- about what
+re-uploading the image costs -- so a script frame is 5-20 % slower with it (bench.py `dropin` block).  The way to stop paying
+for uploads is the device-resident API (INTEGRATION.md level 3), not a cache in front of a host-array API.
 """
 import numpy as np
 import torch
@@ -64,19 +68,30 @@ class _Entry:
         self.eig = {}        # blockSize -> min-eigenvalue map
 
 
+def _same_bytes(a, b):
+    """exact content comparison of two equally shaped uint8 arrays (8 bytes at a time when both are contiguous)"""
+    if a.flags["C_CONTIGUOUS"] and b.flags["C_CONTIGUOUS"]:
+        fa, fb = a.reshape(-1), b.reshape(-1)
+        n8 = fa.size & ~7
+        if n8 and not np.array_equal(fa[:n8].view(np.uint64), fb[:n8].view(np.uint64)):
+            return False
+        return n8 == fa.size or np.array_equal(fa[n8:], fb[n8:])
+    return np.array_equal(a, b)
+
+
 class _ImageCache:
     """Most-recently-used list of host images with their device-resident products."""
 
     def __init__(self, capacity):
         self.capacity = capacity
         self.items = []
+        self.spare = []          # private host buffers of evicted entries, reused to avoid an allocation per frame
         self.hits = self.misses = 0
 
     @staticmethod
     def _sig(a):
-        # a few rows as a cheap first test; the decision is always the full comparison below
-        h = a.shape[0]
-        return a[:: max(1, h // 4)].tobytes()
+        # one row as a cheap first test; the decision is always the full comparison below
+        return a[a.shape[0] // 2].tobytes()
 
     def find(self, a):
         sig = None
@@ -85,7 +100,7 @@ class _ImageCache:
                 continue
             if sig is None:
                 sig = self._sig(a)
-            if e.sig == sig and np.array_equal(e.host, a):
+            if e.sig == sig and _same_bytes(e.host, a):
                 if i:
                     self.items.insert(0, self.items.pop(i))
                 self.hits += 1
@@ -94,13 +109,24 @@ class _ImageCache:
         return None
 
     def add(self, a, dev):
-        e = _Entry(np.array(a, copy=True), self._sig(a), dev)
+        buf = None
+        for i, s in enumerate(self.spare):
+            if s.shape == a.shape and s.dtype == a.dtype:
+                buf = self.spare.pop(i)
+                break
+        if buf is None:
+            buf = np.empty_like(a, order="C")
+        np.copyto(buf, a)
+        e = _Entry(buf, self._sig(a), dev)
         self.items.insert(0, e)
+        for old in self.items[self.capacity:]:
+            if len(self.spare) < 4:
+                self.spare.append(old.host)
         del self.items[self.capacity:]
         return e
 
 
-_cache_on = True
+_cache_on = False     # measured on B200 (bench.py `dropin`): a re-upload + recompute is cheaper than the host-side byte comparison
 _images = _ImageCache(6)      # frames: prev, next, the gray intermediate, a few spares
 _masks = _ImageCache(8)       # ROI masks (the scripts use four)
 
@@ -115,6 +141,7 @@ def cache_enable(on=True):
 def cache_clear():
     _images.items.clear()
     _masks.items.clear()
+    _images.spare.clear()
     _images.hits = _images.misses = _masks.hits = _masks.misses = 0
 
 

@@ -124,7 +124,7 @@ def pyrlk(prev_pyr, next_pyr, pts, params, counts=None, next_pts=None, want_iter
         nxt = next_pts.clone() if next_pts is not None else torch.empty_like(pts)
         st = torch.empty((B, N), dtype=torch.uint8, device=dev)
         err = torch.empty((B, N), dtype=torch.float32, device=dev)
-    iters = torch.empty((B, N), dtype=torch.int32, device=dev) if want_iters else None
+    iters = torch.zeros((B, N), dtype=torch.int32, device=dev) if want_iters else None      # points beyond counts[b] stay 0
     Arr = LkfImage * n_levels
     pa = Arr(*[image_desc(t) for t in prev_pyr])
     na = Arr(*[image_desc(t) for t in next_pyr])

@@ -185,6 +185,9 @@ class PairPipeline:
     # -- CUDA graph ------------------------------------------------------------------------------
     def capture(self, bgr):
         """Record one step on `bgr` (a persistent input buffer) into a CUDA graph; returns replay()."""
+        if self.R:
+            self.stage_refresh_detect()      # eager: sizes this workspace's scratch (a captured call may not grow it); its
+                                             # outputs are rewritten by every replay
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

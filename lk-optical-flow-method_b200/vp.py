@@ -147,7 +147,8 @@ class ClipBatchRunner:
         st0 = LkfVpState()
         st0.avg_len[0] = st0.avg_len[1] = float(cfg["MIN_FL_LEN"])
         raw = np.frombuffer(bytes(st0), dtype=np.uint8)
-        self.states = torch.from_numpy(np.tile(raw, (B, 1)).copy()).to(self.dev)          # [B, sizeof(state)] bytes
+        self._state0 = torch.from_numpy(np.tile(raw, (B, 1)).copy()).to(self.dev)
+        self.states = self._state0.clone()                                                # [B, sizeof(state)] bytes
         self.vp_params = LkfVpParams(
             cp_gate_x=self.WID * cfg["CP_THOLD"], cp_gate_y=self.Hei * cfg["CP_THOLD"], min_ang_dif=float(cfg["MIN_ANG_DIF"]),
             max_cp_std=float(cfg["MAX_CP_STD"]), vp_update_rate=float(cfg["VP_UPDATE_RATE"]),
@@ -180,6 +181,15 @@ class ClipBatchRunner:
         check(self.ws.lib.lkf_vp_apply_refresh(self.states.data_ptr(), self.B, self.corners.data_ptr(), self.ccounts.data_ptr(),
                                                self.maxc, self.p0.data_ptr(), self.counts.data_ptr(), self.maxp,
                                                1 if force else 0, stream_ptr()), "lkf_vp_apply_refresh")
+
+    def reset(self):
+        """Back to the state before start(): a new batch of clips of the same geometry on the same buffers (the CUDA
+        graphs of step_graph stay valid: they hold buffer addresses, not clip state)."""
+        self.states.copy_(self._state0)
+        for t in (self.p0, self.p1, self.st, self.err, self.counts, self.refresh, self.ccounts):
+            t.zero_()
+        self.cur = 0
+        self.frames_done = 0
 
     # -- the frame loop -----------------------------------------------------------------------------
     def start(self, first_frames):
@@ -243,6 +253,8 @@ class ClipBatchRunner:
         rows = self.rows.cpu().numpy()
         out = []
         for b, s in enumerate(sts):
+            if s.row_overflow & 2:
+                raise RuntimeError(f"clip {b}: the corner selection of a refresh overflowed its candidate capacity")
             if s.row_overflow:
                 raise RuntimeError(f"clip {b}: CSV row capacity {self.row_cap} exceeded; pass a larger row_capacity")
             out.append(rows[b, :s.n_rows].copy())

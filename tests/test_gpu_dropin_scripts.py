@@ -35,7 +35,7 @@ def test_unmodified_script_under_patch(name, tmp_path):
     for t, f in enumerate(_clip(meta)):
         cv2.imwrite(str(tmp_path / f"f_{t:04d}.png"), f)
     lib = Workspace.current().lib
-    b200.cache_clear()
+    b200.cache_enable(True)
     n0 = lib.lkf_ctx_launch_count(None)
     saved = b200.patch(cv2)
     try:
@@ -43,7 +43,9 @@ def test_unmodified_script_under_patch(name, tmp_path):
     finally:
         b200.unpatch(cv2, saved)
     assert lib.lkf_ctx_launch_count(None) > n0          # the CUDA path really ran inside the script
-    assert b200.cache_stats()["image_hits"] > meta["frames"]
+    hits = b200.cache_stats()["image_hits"]
+    b200.cache_enable(False)
+    assert hits > meta["frames"]
     assert text.startswith("x,y\r\n")
     got = np.loadtxt(text.splitlines()[1:], delimiter=",").reshape(-1, 2) if text.count("\n") > 1 else np.zeros((0, 2))
     gold = np.loadtxt(os.path.join(GOLD, f"{name}.csv"), delimiter=",", skiprows=1).reshape(-1, 2)
@@ -106,7 +108,7 @@ def test_work_cache_launches_per_script_frame():
     ref, g0, l0 = run(False)
     got, g1, l1 = run(True)
     st = cv.cache_stats()
-    cv.cache_enable(True)
+    cv.cache_enable(False)
     for a, b in zip(ref, got):
         assert np.array_equal(a, b)
     assert len(ref[0]) >= 8
@@ -136,7 +138,6 @@ def test_cache_never_returns_a_stale_image():
     c = cv.goodFeaturesToTrack(g, 50, 0.05, 5, blockSize=3)
     cv.cache_enable(False)
     d = cv.goodFeaturesToTrack(g, 50, 0.05, 5, blockSize=3)
-    cv.cache_enable(True)
     assert not np.array_equal(a, b) and np.array_equal(b, c) and np.array_equal(c, d)
 
 

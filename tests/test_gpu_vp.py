@@ -54,16 +54,18 @@ def _random_tracks(rng, mask, n, foe, lose=0.15, outside=0.1, still=0.05):
     return p0, p1, st
 
 
-@pytest.mark.parametrize("variant,tp_num,seed", [("VP", 20, 0), ("LKF", 20, 1), ("VP", 100, 2), ("VP", 20, 3)])
-def test_vp_frame_kernel_matches_oracle(variant, tp_num, seed):
+@pytest.mark.parametrize("variant,tp_num,seed,vp_ref", [("VP", 20, 0, 300), ("LKF", 20, 1, 300), ("VP", 100, 2, 300), ("VP", 20, 3, 300),
+                                                        ("VP", 20, 4, 0)])
+def test_vp_frame_kernel_matches_oracle(variant, tp_num, seed, vp_ref):
+    # vp_ref = 0: the reference documents VP_REF = 0 as "use all VPs" (all_vp[-0:] is the whole history)
     import torch
     from lk_optical_flow_method_b200 import vp as V
     from oracle import vp_oracle as O
     mask, small = _masks()
     B, frames = 3, 140
     r = V.ClipBatchRunner(B, (720, 1280), variant=variant,   # Hei = int(860*720/1280) = 483 like the script
-                          masks=(mask, small), TP_NUM=tp_num, expected_frames=frames + 8)
-    p = O.params(variant, TP_NUM=tp_num)
+                          masks=(mask, small), TP_NUM=tp_num, VP_REF=vp_ref, expected_frames=frames + 8)
+    p = O.params(variant, TP_NUM=tp_num, VP_REF=vp_ref)
     S = [O.new_state(p) for _ in range(B)]
     rng = np.random.default_rng(seed)
     maxp = r.maxp
