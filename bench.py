@@ -368,7 +368,7 @@ def c5_block(args, rank, world, dev):
     import torch
     import torch.distributed as dist
     from lk_optical_flow_method_b200 import shard, synth
-    n_clips, n_frames = 64, 17
+    n_clips, n_frames = 64, 33
     texs = [torch.from_numpy(synth.make_texture(W, H, 100 + k)).to(dev) for k in range(4)]
     mine = shard.assign(n_clips, world, rank)
     host_group = dist.new_group(backend="gloo") if world > 1 else None
@@ -378,7 +378,9 @@ def c5_block(args, rank, world, dev):
         dist.barrier()
     t0 = time.perf_counter()
     rows, dev_s = c5_run(mine, runner, buf, batches)
-    merged = shard.gather_to_root(rows, group=host_group) if world > 1 else rows
+    n_rows_local = sum(len(v) for v in rows.values())
+    texts = shard.render_csvs(rows)                       # every rank formats its own clips
+    merged = shard.gather_to_root(texts, group=host_group) if world > 1 else texts
     sha = None
     if rank == 0:
         paths = shard.write_vp_csvs(merged, [f"clip{c:02d}" for c in range(n_clips)], out_dir)
@@ -390,15 +392,17 @@ def c5_block(args, rank, world, dev):
         dist.barrier()
     total_s = time.perf_counter() - t0
     t = torch.tensor([total_s, dev_s], dtype=torch.float64, device=dev)
+    nr = torch.tensor([n_rows_local], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nr, op=dist.ReduceOp.SUM)
     res = None
     if rank == 0:
         total_s, dev_s = float(t[0]), float(t[1])
-        n_rows = int(sum(len(v) for v in merged.values()))
+        n_rows = int(nr.item())
         res = {"clips": n_clips, "frames_per_clip": n_frames, "ranks": world, "clips_per_rank": len(mine),
                "clip_frames_per_s": n_clips * n_frames / total_s, "seconds": total_s, "device_seconds_max_rank": dev_s,
-               "csv_rows": n_rows, "csv_sha256": sha, "gather": "gloo gather_object to rank 0 + one CSV per clip (save_csv schema)",
+               "csv_rows": n_rows, "csv_sha256": sha, "gather": "every rank renders its clips' CSV text; gloo gather_object to rank 0, which writes one file per clip (save_csv schema)",
                "timed": "first frame of every clip -> CSV files written; frames resident in HBM, step graphs captured beforehand; max "
                         "over ranks (wall clock: it includes the D2H of the rows, the host gather and the file writes)"}
         if world > 1:

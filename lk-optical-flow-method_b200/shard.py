@@ -33,13 +33,22 @@ def gather_to_root(local_results, root=0, group=None):
 
 
 def write_vp_csvs(rows_by_clip, names, out_dir):
-    """One ./vps/vps_<name>.csv per clip with the reference's schema (save_csv, VP.py:388-392)."""
+    """One ./vps/vps_<name>.csv per clip with the reference's schema (save_csv, VP.py:388-392).  A value may be the rows
+    of a clip or its CSV text already rendered by the rank that tracked it (render_csvs)."""
     from .vp import csv_text
     os.makedirs(out_dir, exist_ok=True)
     paths = []
     for c in sorted(rows_by_clip):
         path = os.path.join(out_dir, f"vps_{names[c]}.csv")
+        v = rows_by_clip[c]
         with open(path, "w", newline="") as f:
-            f.write(csv_text(rows_by_clip[c]))
+            f.write(v if isinstance(v, str) else csv_text(v))
         paths.append(path)
     return paths
+
+
+def render_csvs(rows_by_clip):
+    """{clip: rows} -> {clip: CSV text}: formatting the rows is host work that shards with the clips, so every rank
+    renders its own and the root only writes files."""
+    from .vp import csv_text
+    return {c: csv_text(r) for c, r in rows_by_clip.items()}

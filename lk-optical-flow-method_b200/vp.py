@@ -66,7 +66,18 @@ def roi_masks(WID, Hei):
 
 
 def csv_text(rows):
-    """save_csv (VP.py:388-392): header `x,y`, one row per VP history entry, csv default dialect (\\r\\n)."""
+    """save_csv (VP.py:388-392): header `x,y`, one row per VP history entry, csv default dialect (\\r\\n).
+    csv.writer writes str(np.float64) for every field, which is the shortest round-trip repr -- the same text as repr() of
+    the Python float (tests/test_host_logic.py compares the two on edge values) -- so the rows are formatted directly
+    (10x faster than csv.writer on the 3 000 rows per second of a 64-clip batch)."""
+    a = np.asarray(rows, dtype=np.float64).reshape(-1, 2)
+    if a.size == 0:
+        return "x,y\r\n"
+    return "x,y\r\n" + "\r\n".join(f"{x!r},{y!r}" for x, y in a.tolist()) + "\r\n"
+
+
+def csv_text_reference(rows):
+    """The same text through csv.writer exactly as the scripts write it (VP.py:388-392); kept as the checker of csv_text."""
     buf = io.StringIO(newline="")
     wr = csv.writer(buf)
     wr.writerow(["x", "y"])

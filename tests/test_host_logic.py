@@ -84,3 +84,18 @@ def test_vanishing_line_endpoints_match_the_oracle_restatement():
         # the recorded end points are the script's own (VP.py:241-244)
         assert st is True and lp == (0, vl["lp_y"]) and rp == (859, vl["rp_y"]) and up == (vl["up_x"], 0) and dp == (vl["dp_x"], 482)
         assert abs(vl["lp_y"] - (vl["bp_y"] - vl["bp_x"] * vl["m"])) < 1e-9
+
+
+def test_csv_text_equals_csv_writer_on_edge_values():
+    """csv_text formats the rows itself; it must give the bytes csv.writer gives for np.float64 fields (save_csv, VP.py:388-392)."""
+    from lk_optical_flow_method_b200 import vp as V
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.uniform(-1e3, 1e3, 4000), rng.uniform(-1, 1, 500) * 10.0 ** rng.integers(-30, 30, 500),
+                           np.array([0.0, -0.0, 1.0, 1e16, 1e15, 123456789012345678.0, 1e-4, 1e-5, 9.999e-5, np.inf, -np.inf, np.nan,
+                                     412.7707922, 289.99299469, 5e-324, 1.7976931348623157e308, 0.1, 1 / 3, 2 ** 53, 1e22, 1e21])])
+    if len(vals) % 2:
+        vals = vals[:-1]
+    rows = vals.reshape(-1, 2)
+    assert V.csv_text(rows) == V.csv_text_reference(rows)
+    assert V.csv_text(np.zeros((0, 2))) == V.csv_text_reference([]) == "x,y\r\n"
+    assert V.csv_text([(1.5, 2.0)]) == "x,y\r\n1.5,2.0\r\n"
