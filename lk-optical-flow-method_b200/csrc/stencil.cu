@@ -3,6 +3,8 @@
 // Structure: shared-memory tiles with halos, 4-byte aligned bodies loaded as 32-bit words, REFLECT_101 by
 // index mirroring (the mirror source of a 1..2-px halo is always inside the image).
 #include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -444,6 +446,227 @@ __global__ void __launch_bounds__(SV_NT, 8) k_pyrdown_stream(const uint8_t *__re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a3, TMA form (sm_100a): the source rows of a CTA's segment arrive in shared memory by cp.async.bulk.tensor
+// (one producer lane, NST-deep ring of 8-row stages, mbarrier full/empty handshake); the 4 consumer warps keep
+// the same arithmetic as k_pyrdown_stream (a thread owns 8 output columns and slides down, DP4A horizontal
+// sums packed two per register, five rows of them in registers), but never issue a global load: no
+// long-scoreboard stalls, the loads of a segment run NST stages ahead of the arithmetic.
+//   tensor map: 3D (W, H, B) uint8, box 256 x 8 x 1, out-of-bounds elements zero-filled.
+//   CTA = (image b, column strip of 1920 source columns, PT_SEG output rows).  Stage j holds source rows
+//   [2 y0 - 3 + 8 j, +8): one dummy row, the three prologue rows 2y0-2..2y0, then whole row pairs, so a
+//   stage boundary never splits the two source rows of an output row.
+//   REFLECT_101: left/right like the streaming kernel (resolved in registers by the edge threads); rows
+//   above/below the image (first/last segment only) are read with ordinary mirrored loads.
+// ---------------------------------------------------------------------------------------------
+constexpr int PT_ROWS = 8, PT_NST = 3, PT_SEG_MAX = 46, PT_STRIP = 1920, PT_MAXW = 4;      // up to 4 consumer warps + 1 producer warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int x, int y, int z, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__((PT_MAXW + 1) * 32, 6)
+k_pyrdown_tma(const __grid_constant__ CUtensorMap map, const uint8_t *__restrict__ src, long long srp, long long sip,
+              uint8_t *__restrict__ dst, long long drp, long long dip, int Hs, int Ws, int Hd, int Wd, int n_boxes,
+              int strips, int segs_per_image, int n_segments, int PT_SEG)
+{
+    extern __shared__ __align__(1024) unsigned char pt_smem[];
+    __shared__ __align__(8) unsigned long long bars[2 * PT_NST];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cw = (blockDim.x >> 5) - 1;                                  // consumer warps; the last warp is the producer
+    const int PT_STAGE_BYTES = n_boxes * 256 * PT_ROWS;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[PT_NST]);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < PT_NST; i++) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, cw); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t buf0 = smem_u32(pt_smem);
+    // PERSISTENT: this CTA owns segments blockIdx.x, blockIdx.x + gridDim.x, ...; segment = (image, strip, PT_SEG output rows).
+    // The producer runs up to PT_NST stages ahead ACROSS segment boundaries, so the ring never drains between segments.
+    auto seg_geom = [&](int g, int &b, int &x0, int &y0, int &y1, int &n_stages) {
+        const int per_img = strips * segs_per_image;
+        b = g / per_img;
+        const int r = g - b * per_img, sx = r % strips, sy = r / strips;
+        x0 = sx * PT_STRIP;
+        y0 = sy * PT_SEG; y1 = min(Hd, y0 + PT_SEG);
+        n_stages = (2 * (y1 - y0) + 4 + PT_ROWS - 1) / PT_ROWS;           // dummy row + rows 2y0-2 .. 2(y1-1)+2
+    };
+
+    if (warp == cw) {
+        if (lane == 0) {
+            int js = 0;                                                    // stages issued by this CTA so far
+            for (int g = blockIdx.x; g < n_segments; g += gridDim.x) {
+                int b, x0, y0, y1, n_stages;
+                seg_geom(g, b, x0, y0, y1, n_stages);
+                for (int j = 0; j < n_stages; j++, js++) {
+                    const int st = js % PT_NST;
+                    if (js >= PT_NST) mbar_wait(empty0 + 8 * st, ((js / PT_NST) - 1) & 1);
+                    mbar_expect_tx(full0 + 8 * st, (uint32_t)n_boxes * 256u * PT_ROWS);
+                    for (int k = 0; k < n_boxes; k++)
+                        tma_load_3d(buf0 + st * PT_STAGE_BYTES + k * 256 * PT_ROWS, &map, x0 - 16 + 256 * k, 2 * y0 - 3 + PT_ROWS * j, b,
+                                    full0 + 8 * st);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: a thread owns 16 source / 8 output columns of the strip ----
+    // a box is stored as PT_ROWS rows of 256 bytes; source column c of the strip (relative to x0 - 16) lives in box c >> 8
+    const int c_main = 16 + 16 * tid;
+    const int off_main = (c_main >> 8) * 256 * PT_ROWS + (c_main & 255);
+    const int off_left = ((c_main - 4) >> 8) * 256 * PT_ROWS + ((c_main - 4) & 255);
+    const int off_right = ((c_main + 16) >> 8) * 256 * PT_ROWS + ((c_main + 16) & 255);
+    int js = 0;
+    for (int g = blockIdx.x; g < n_segments; g += gridDim.x) {
+        int b, x0, y0, y1, n_stages;
+        seg_geom(g, b, x0, y0, y1, n_stages);
+        const int base = 2 * y0 - 3;
+        const int xs = x0 + 16 * tid;
+        const bool active = xs < Ws && xs < x0 + PT_STRIP;
+        const bool has_left = xs > 0, has_right = xs + 16 < Ws;
+        const bool interior = base + 1 >= 0 && base + PT_ROWS * n_stages <= Hs;     // every row the segment reads is in the image
+        const uint8_t *S = src + (long long)b * sip;
+        uint8_t *drow = dst + (long long)b * dip + (long long)y0 * drp + (xs >> 1);
+        auto row_fast = [&](const unsigned char *row) -> PdRaw {
+            PdRaw q;
+            q.v = *reinterpret_cast<const uint4 *>(row + off_main);
+            q.l = has_left ? *reinterpret_cast<const uint32_t *>(row + off_left) : __byte_perm(q.v.x, 0u, 0x1200);
+            q.r = has_right ? (uint32_t)row[off_right] : (q.v.w >> 16) & 255u;
+            return q;
+        };
+        auto row_any = [&](const unsigned char *row, int t) -> PdRaw {     // mirrored rows: first / last segment of an image
+            if (t < 0 || t >= Hs) return pd_load_row(S, srp, t, Hs, xs, Ws);
+            return row_fast(row);
+        };
+        auto vstore = [&](const uint32_t (&a)[4], const uint32_t (&bb)[4], const uint32_t (&c)[4], const uint32_t (&d)[4],
+                          const uint32_t (&e)[4]) {
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                o[k] = ((a[k] + e[k] + 0x00800080u + 4u * (bb[k] + d[k]) + 6u * c[k]) >> 8) & 0x00ff00ffu;
+            *reinterpret_cast<uint2 *>(drow) = make_uint2(__byte_perm(o[0], o[1], 0x6420), __byte_perm(o[2], o[3], 0x6420));
+            drow += drp;
+        };
+        uint32_t r0[4], r1[4], r2[4], r3[4], r4[4];
+        int y = y0;
+        for (int j = 0; j < n_stages; j++, js++) {
+            const int st = js % PT_NST;
+            mbar_wait(full0 + 8 * st, (js / PT_NST) & 1);
+            const unsigned char *stage = pt_smem + st * PT_STAGE_BYTES;
+            const int t0 = base + PT_ROWS * j;
+            if (active) {
+                if (interior && j > 0 && y + 4 <= y1) {                    // steady state: four row pairs, no tests
+#pragma unroll
+                    for (int rr = 0; rr < PT_ROWS; rr += 2) {
+                        pd_hsum_row(row_fast(stage + rr * 256), r3);
+                        pd_hsum_row(row_fast(stage + (rr + 1) * 256), r4);
+                        vstore(r0, r1, r2, r3, r4);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) { r0[k] = r2[k]; r1[k] = r3[k]; r2[k] = r4[k]; }
+                    }
+                    y += 4;
+                } else {
+                    int r = 0;
+                    if (j == 0) {                                          // rows 1..3 of stage 0: the prologue rows 2y0-2 .. 2y0
+                        pd_hsum_row(row_any(stage + 256, t0 + 1), r0);
+                        pd_hsum_row(row_any(stage + 512, t0 + 2), r1);
+                        pd_hsum_row(row_any(stage + 768, t0 + 3), r2);
+                        r = 4;
+                    }
+#pragma unroll 1
+                    for (int rr = r; rr < PT_ROWS && y < y1; rr += 2) {
+                        pd_hsum_row(row_any(stage + rr * 256, t0 + rr), r3);
+                        pd_hsum_row(row_any(stage + (rr + 1) * 256, t0 + rr + 1), r4);
+                        vstore(r0, r1, r2, r3, r4);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) { r0[k] = r2[k]; r1[k] = r3[k]; r2[k] = r4[k]; }
+                        y++;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * st);
+        }
+    }
+}
+
+typedef CUresult (*lkf_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static lkf_encode_tiled_fn encode_tiled()
+{
+    static lkf_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (lkf_encode_tiled_fn)p;
+        tried = true;
+    }
+    return fn;
+}
+
+// 1 = launched, 0 = geometry not eligible (caller falls back to the streaming kernel), < 0 = error
+static int launch_pyrdown_tma(const lkf_image *src, const lkf_image *dst, cudaStream_t s)
+{
+    if (src->width % 16 || src->width < 32 || src->height < 8 || !aligned_to(src, 16) || !aligned_to(dst, 8)) return 0;
+    if (src->batch > 1 && src->image_pitch % 16) return 0;
+    lkf_encode_tiled_fn enc = encode_tiled();
+    if (!enc) return 0;
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {(cuuint64_t)src->width, (cuuint64_t)src->height, (cuuint64_t)src->batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)src->row_pitch, (cuuint64_t)(src->batch > 1 ? src->image_pitch : src->row_pitch * src->height)};
+    const cuuint32_t box[3] = {256, PT_ROWS, 1}, estr[3] = {1, 1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, src->data, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    const int strips = (src->width + PT_STRIP - 1) / PT_STRIP;
+    const int strip_w = src->width < PT_STRIP ? src->width : PT_STRIP;
+    const int n_boxes = (strip_w + 32 + 255) / 256;                        // columns x0-16 .. x0+strip+16
+    const int cw = (strip_w / 16 + 31) / 32;                               // consumer warps: 16 source columns per thread
+    const int nt = (cw + 1) * 32;
+    const size_t smem = (size_t)PT_NST * n_boxes * 256 * PT_ROWS + 1024;
+    LKF_FUNC_ATTRS(LKF_CUDA(cudaFuncSetAttribute(k_pyrdown_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pyrdown_tma, nt, smem);
+    if (per_sm < 1) return 0;
+    const long long resident = (long long)per_sm * sms;                    // persistent: every CTA is resident
+    // output rows per segment: 2 + 4m (stage 0 yields two rows, every later stage four); as long as possible while the
+    // segments still fill the resident CTAs about three times over
+    int seg = PT_SEG_MAX;
+    while (seg > 6 && (long long)strips * ((dst->height + seg - 1) / seg) * dst->batch < 3 * resident) seg -= 4;
+    const int segs = (dst->height + seg - 1) / seg;
+    const long long n_seg = (long long)strips * segs * dst->batch;
+    const int grid = (int)(n_seg < resident ? n_seg : resident);
+    k_pyrdown_tma<<<grid, nt, smem, s>>>(map, (const uint8_t *)src->data, src->row_pitch, src->image_pitch, (uint8_t *)dst->data,
+                                         dst->row_pitch, dst->image_pitch, src->height, src->width, dst->height, dst->width, n_boxes,
+                                         strips, segs, (int)n_seg, seg);
+    return 1;
+}
+
 bool same_geometry(const lkf_image *a, const lkf_image *b)
 {
     return a->batch == b->batch && a->height == b->height && a->width == b->width;
@@ -499,6 +722,15 @@ LKF_EXPORT int lkf_pyr_down_u8(const lkf_image *src, const lkf_image *dst, lkf_s
     if (!img_ok(src, 1, 1) || !img_ok(dst, 1, 1) || src->batch != dst->batch ||
         dst->height != (src->height + 1) / 2 || dst->width != (src->width + 1) / 2)
         return LKF_ERR_ARG;
+    // TMA form for wide levels (measured, 65 frames of 1920x1080 -> 960x540: 34.8-35.2 us vs 39.8 us for the streaming kernel;
+    // 960x540 -> 480x270: 14.0 vs 13.5 us, so narrow levels keep the streaming kernel).  LKF_PYR_TMA=0/1 forces one form
+    // (developer switch for A/B timing, read once).
+    static const int force_tma = getenv("LKF_PYR_TMA") ? atoi(getenv("LKF_PYR_TMA")) : -1;
+    if (force_tma == 1 || (force_tma < 0 && src->width >= 1280)) {
+        const int rc = launch_pyrdown_tma(src, dst, (cudaStream_t)stream);
+        if (rc < 0) return rc;
+        if (rc == 1) { LKF_LAUNCH_CHECK(nullptr); return LKF_OK; }
+    }
     if (src->width % 16 == 0 && src->width >= 32 && src->height >= 4 && aligned_to(src, 16) && aligned_to(dst, 8)) {
         // rows per CTA: 16, fewer when that leaves the GPU short of about one wave of resident warps (small levels)
         const int nt = stream_threads(dst->width / 8);
