@@ -114,6 +114,17 @@ int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *params, int n_levels,
                      float *next_pts, uint8_t *status, float *err, int32_t *iters,
                      lkf_stream stream);
 
+/* ---- a7 on the raster grid (BASELINE config C4, dense per-pixel flow): the same tracker for
+ *      prevPts = every pixel (x, y) of level 0, in raster order; no point array is read.  Outputs hold
+ *      height*width entries per image (next_pts [B][H*W][2], status, err, iters), bit-identical to
+ *      lkf_pyrlk_sparse on those points.  Supported: odd square windows 3/5/7, at most 4 levels,
+ *      flags without LKF_OPTFLOW_USE_INITIAL_FLOW (LKF_ERR_UNSUPPORTED otherwise).
+ *      lkf_pyrlk_sparse itself switches to this kernel when it is handed exactly that grid (checked
+ *      on the device, no host round trip). */
+int lkf_pyrlk_dense(lkf_ctx *ctx, const lkf_lk_params *params, int n_levels,
+                    const lkf_image *prev_pyr, const lkf_image *next_pyr,
+                    float *next_pts, uint8_t *status, float *err, int32_t *iters, lkf_stream stream);
+
 /* ---- a5: cornerMinEigenVal inside cv.goodFeaturesToTrack          VP.py:503,707 ------------- */
 int lkf_corner_min_eigen_f32(const lkf_image *src_u8, const lkf_image *eig_f32, int block_size,
                              int dy_tail_cols, lkf_stream stream);

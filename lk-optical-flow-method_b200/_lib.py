@@ -89,6 +89,7 @@ SIGNATURES = {
     "lkf_effective_max_level": (_i, [_i, _i, _i, _i, _i]),
     "lkf_pyrlk_sparse": (_i, [_vp, _P(LkfLkParams), _i, _P(LkfImage), _P(LkfImage), _vp, _vp, _i,
                               _vp, _vp, _vp, _vp, _vp]),
+    "lkf_pyrlk_dense": (_i, [_vp, _P(LkfLkParams), _i, _P(LkfImage), _P(LkfImage), _vp, _vp, _vp, _vp, _vp]),
     "lkf_corner_min_eigen_f32": (_i, [_P(LkfImage), _P(LkfImage), _i, _i, _vp]),
     "lkf_probe_fp32_fma": (_i, [_i, _i, _vp, _vp]),
     "lkf_probe_pipe": (_i, [_i, _i, _i, _vp, _vp]),

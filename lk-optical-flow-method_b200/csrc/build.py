@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "liblkflow_b200.so")
-SOURCES = ["abi.cu", "stencil.cu", "lk.cu", "gftt.cu", "vp.cu", "probe.cu", "resize.cu"]
+SOURCES = ["abi.cu", "stencil.cu", "lk.cu", "lk_dense.cu", "gftt.cu", "vp.cu", "probe.cu", "resize.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "--extended-lambda", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]

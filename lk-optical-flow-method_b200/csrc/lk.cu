@@ -11,75 +11,12 @@
 //      the same way.  All float32 scalar steps use explicitly rounded intrinsics (no FMA contraction)
 //      so they follow cv2's float32 sequence; only the (exact) integer sums replace cv2's float32
 //      lane accumulation (difference <= 3e-4 px, see tests).
-#include "common.cuh"
-#include <limits.h>
+#include "lk_common.cuh"
 
 namespace {
 
 constexpr int LK_WARPS = 8;
 
-struct LKLevels {
-    const uint8_t *prev[LKF_MAX_LEVELS];
-    const uint8_t *next[LKF_MAX_LEVELS];
-    long long prp[LKF_MAX_LEVELS], pip[LKF_MAX_LEVELS], nrp[LKF_MAX_LEVELS], nip[LKF_MAX_LEVELS];
-    int H[LKF_MAX_LEVELS], W[LKF_MAX_LEVELS];
-};
-
-__device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
-
-// exact warp sum of int32 lane partials -> int64 (two REDUX instructions)
-__device__ __forceinline__ long long warp_sum(int v)
-{
-    int hi = __reduce_add_sync(0xffffffffu, v >> 16);
-    unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xffff));
-    return ((long long)hi << 16) + (long long)lo;
-}
-__device__ __forceinline__ long long warp_sum(long long v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// cv2: delta.ddot(delta) <= epsilon, the dot product accumulated in double.  A float32 estimate decides all but the
-// borderline cases (relative error of the estimate < 3e-7), which take the exact double path.
-// (the float bounds are prepared on the host: kernel parameters cost neither registers nor instructions per iteration)
-struct LKEps {
-    double e2;          // epsilon^2 after cv2's clamping
-    float lo, hi;       // (float)e2 * 0.999999f, (float)e2 * 1.000001f
-};
-static inline LKEps make_eps(double e2)
-{
-    LKEps r;
-    r.e2 = e2;
-    const float e = (float)e2;
-    r.lo = e * 0.999999f; r.hi = e * 1.000001f;
-    return r;
-}
-__device__ __forceinline__ bool lk_step_below_eps(float dx, float dy, const LKEps &eps)
-{
-    const float f = dx * dx + dy * dy;
-    if (f < eps.lo) return true;
-    if (f > eps.hi) return false;
-    return __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps.e2;
-}
-// cv2: std::abs(x) < 0.01 with a float x and the double constant 0.01: the largest float below 0.01 is fl(0.01)
-__device__ __forceinline__ bool lk_below_001(float x) { return fabsf(x) <= 0.00999999977648258209228515625f; }
-
-__device__ __forceinline__ void weights(float a, float b, int &w00, int &w01, int &w10, int &w11)
-{
-    float na = __fsub_rn(1.f, a), nb = __fsub_rn(1.f, b);
-    w00 = __float2int_rn(__fmul_rn(__fmul_rn(na, nb), 16384.f));
-    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, nb), 16384.f));
-    w10 = __float2int_rn(__fmul_rn(__fmul_rn(na, b), 16384.f));
-    w11 = 16384 - w00 - w01 - w10;
-}
-
-__device__ __forceinline__ bool out_of_level(float fx, float fy, int ix, int iy, int w, int h, int W, int H)
-{
-    // non-finite coordinates behave like cv2 on x86 (cvFloor -> INT_MIN -> rejected)
-    return !(isfinite(fx) && isfinite(fy)) || ix < -w || ix >= W || iy < -h || iy >= H;
-}
 
 // Sum over the window of f(sample of J at the window pixel, template index).  Fast path when the
 // (w+1)x(h+1) footprint is inside the level, mirrored indexing otherwise (warp-uniform choice).
@@ -323,19 +260,6 @@ struct LKT {
     static_assert(RWW <= 16 && TILE_WPR <= 32, "loader lane mapping");
 };
 
-// two-way dot product: signed 16-bit halves of `a` (Q14 weights, -1..16384) times unsigned bytes 0,1 (lo) / 2,3 (hi) of `b`
-__device__ __forceinline__ int dp2a_lo(int a, unsigned b, int c)
-{
-    int d;
-    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ int dp2a_hi(int a, unsigned b, int c)
-{
-    int d;
-    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
@@ -906,73 +830,17 @@ int launch_lk_t(const LKLevels &lv, int n_levels, int max_count, double eps, con
 // all window sums are exact int32 (AREA <= 49), everything is unrolled at compile time.  Same arithmetic and
 // control flow as the warp kernels: results are bit-identical to them.
 // ---------------------------------------------------------------------------------------------
-template <int NB>
-__device__ __noinline__ void load_row_bytes_edge(const uint8_t *__restrict__ row, int W, int gx, uint32_t *w)
-{   // cold: the row segment touches the border of the level (or the plane is not 4-byte aligned)
-#pragma unroll 1
-    for (int i = 0; i < (NB + 3) / 4; i++) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-            if (4 * i + c < NB) v |= (uint32_t)row[reflect101(gx + 4 * i + c, W)] << (8 * c);
-        w[i] = v;
-    }
-}
-
-// NB consecutive bytes of row gy starting at column gx (REFLECT_101 outside the level), packed from byte 0 of w[0]
-template <int NB>
-__device__ __forceinline__ void load_row_bytes(const uint8_t *__restrict__ P, long long rp, int W, int H, bool al4, int gx, int gy,
-                                               uint32_t (&w)[(NB + 3) / 4])
-{
-    constexpr int NW = (NB + 3) / 4;
-    const uint8_t *row = P + (long long)((unsigned)gy < (unsigned)H ? gy : reflect101(gy, H)) * rp;
-    const int ax = (gx >> 2) << 2;
-    if (al4 && ax >= 0 && ax + 4 * (NW + 1) <= W) {
-        const uint32_t *q = reinterpret_cast<const uint32_t *>(row + ax);
-        uint32_t t[NW + 1];
-#pragma unroll
-        for (int i = 0; i <= NW; i++) t[i] = __ldg(q + i);
-        const int sh = (gx & 3) * 8;
-#pragma unroll
-        for (int i = 0; i < NW; i++) w[i] = __funnelshift_r(t[i], t[i + 1], sh);
-    } else {
-        uint32_t tmp[NW];
-        load_row_bytes_edge<NB>(row, W, gx, tmp);
-#pragma unroll
-        for (int i = 0; i < NW; i++) w[i] = tmp[i];
-    }
-}
-template <int NW>
-__device__ __forceinline__ int byte_of(const uint32_t (&w)[NW], int c) { return (int)((w[c >> 2] >> (8 * (c & 3))) & 255u); }
-
-// bilinear Q14 sums of N pixels from two packed byte rows: v[t] = top(t) w00 + top(t+1) w01 + bot(t) w10 + bot(t+1) w11,
-// rounded and shifted to I*32 ((sum + 2^8) >> 9)
-template <int N, int NW>
-__device__ __forceinline__ void bilinear_packed(const uint32_t (&top)[NW], const uint32_t (&bot)[NW], int first, int wT, int wB,
-                                                int (&v)[N])
-{
-#pragma unroll
-    for (int t = 0; t < N; t++) {
-        const int c = first + t, i = c >> 2, j = c & 3;
-        uint32_t wa, wc;
-        if (j & 1) {
-            wa = i + 1 < NW ? __funnelshift_r(top[i], top[i + 1], 8) : top[i] >> 8;
-            wc = i + 1 < NW ? __funnelshift_r(bot[i], bot[i + 1], 8) : bot[i] >> 8;
-        } else { wa = top[i]; wc = bot[i]; }
-        int acc = (j & 2) ? dp2a_hi(wT, wa, 256) : dp2a_lo(wT, wa, 256);
-        v[t] = ((j & 2) ? dp2a_hi(wB, wc, acc) : dp2a_lo(wB, wc, acc)) >> 9;
-    }
-}
 
 template <int WW, int WH>
 __global__ void __launch_bounds__(128)
 k_lk_track_small(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, double min_eig_thr,
                  const float *__restrict__ prev_pts, const int *__restrict__ counts, int max_pts,
                  float *__restrict__ next_pts, uint8_t *__restrict__ status, float *__restrict__ err,
-                 int *__restrict__ iters_out, unsigned al4_mask, unsigned ial4_mask)
+                 int *__restrict__ iters_out, unsigned al4_mask, unsigned ial4_mask, const int *__restrict__ skip_flag)
 {
     constexpr int AREA = WW * WH, RW = WW + 3, NWR = (RW + 3) / 4, NWJ = (WW + 1 + 3) / 4;
     static_assert(AREA <= 49, "exact int32 window sums");
+    if (skip_flag && *skip_flag) return;                  // prevPts is the raster grid: k_lk_dense does this call
     const int pt = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     const int n = counts ? counts[b] : max_pts;
     if (pt >= n || pt >= max_pts) return;
@@ -1140,11 +1008,11 @@ k_lk_track_small(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags
 template <int WW, int WH>
 int launch_lk_small(const LKLevels &lv, int n_levels, int max_count, double eps, const lkf_lk_params *p, const float *prev_pts,
                     const int32_t *pt_counts, int max_pts, float *next_pts, uint8_t *status, float *err, int32_t *iters,
-                    unsigned al4_mask, unsigned ial4_mask, int B, cudaStream_t s)
+                    unsigned al4_mask, unsigned ial4_mask, int B, cudaStream_t s, const int *skip_flag)
 {
     dim3 grid((max_pts + 127) / 128, B);
     k_lk_track_small<WW, WH><<<grid, 128, 0, s>>>(lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, prev_pts, pt_counts,
-                                                  max_pts, next_pts, status, err, iters, al4_mask, ial4_mask);
+                                                  max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, skip_flag);
     return LKF_OK;
 }
 
@@ -1157,6 +1025,56 @@ size_t lk_per_warp_bytes(int w, int h)
 
 }  // namespace
 
+// lk_dense.cu
+bool lk_dense_supported(const lkf_lk_params *p, int n_levels);
+int lk_dense_grid_check(const float *prev_pts, int B, int W, int H, int *flag, cudaStream_t s);
+int lk_dense_launch(const lkf_lk_params *p, int n_levels, const lkf_image *prev_pyr, const lkf_image *next_pyr, int max_count, double eps,
+                    float *next_pts, uint8_t *status, float *err, int32_t *iters, const int *grid_flag, cudaStream_t s);
+
+static void lk_resolve_criteria(const lkf_lk_params *p, int *max_count, double *eps2)
+{   // cv2: missing COUNT -> 30 iterations, missing EPS -> 0.01; clamps as in lkpyramid.cpp; epsilon is squared
+    int mc = p->max_count;
+    double eps = p->epsilon;
+    if (!(p->crit_type & LKF_TERM_CRITERIA_COUNT)) mc = 30;
+    else mc = mc < 0 ? 0 : (mc > 100 ? 100 : mc);
+    if (!(p->crit_type & LKF_TERM_CRITERIA_EPS)) eps = 0.01;
+    else eps = eps < 0 ? 0 : (eps > 10 ? 10 : eps);
+    *max_count = mc; *eps2 = eps * eps;
+}
+
+static int lk_check_pyramids(const lkf_image *prev_pyr, const lkf_image *next_pyr, int n_levels)
+{
+    const int B = prev_pyr[0].batch;
+    for (int l = 0; l < n_levels; l++) {
+        if (!img_ok(&prev_pyr[l], 1, 1) || !img_ok(&next_pyr[l], 1, 1)) return LKF_ERR_ARG;
+        if (prev_pyr[l].batch != B || next_pyr[l].batch != B || prev_pyr[l].height != next_pyr[l].height ||
+            prev_pyr[l].width != next_pyr[l].width)
+            return LKF_ERR_ARG;
+        if (l > 0 && (prev_pyr[l].height != (prev_pyr[l - 1].height + 1) / 2 ||
+                      prev_pyr[l].width != (prev_pyr[l - 1].width + 1) / 2))
+            return LKF_ERR_ARG;
+    }
+    return LKF_OK;
+}
+
+// a7 for prevPts = every pixel (x, y) of level 0 in raster order (config C4); outputs have H*W entries per image
+LKF_EXPORT int lkf_pyrlk_dense(lkf_ctx *ctx, const lkf_lk_params *p, int n_levels, const lkf_image *prev_pyr,
+                               const lkf_image *next_pyr, float *next_pts, uint8_t *status, float *err, int32_t *iters,
+                               lkf_stream stream)
+{
+    if (!p || !prev_pyr || !next_pyr || n_levels < 1 || n_levels > LKF_MAX_LEVELS) return LKF_ERR_ARG;
+    if (p->win_w <= 2 || p->win_h <= 2 || p->max_level < 0 || !next_pts || !status || !err) return LKF_ERR_ARG;
+    int rc = lk_check_pyramids(prev_pyr, next_pyr, n_levels);
+    if (rc != LKF_OK) return rc;
+    if (!lk_dense_supported(p, n_levels)) return LKF_ERR_UNSUPPORTED;
+    int max_count; double eps;
+    lk_resolve_criteria(p, &max_count, &eps);
+    rc = lk_dense_launch(p, n_levels, prev_pyr, next_pyr, max_count, eps, next_pts, status, err, iters, nullptr, (cudaStream_t)stream);
+    if (rc != LKF_OK) return rc;
+    LKF_LAUNCH_CHECK(ctx);
+    return LKF_OK;
+}
+
 LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_levels, const lkf_image *prev_pyr,
                                 const lkf_image *next_pyr, const float *prev_pts, const int32_t *pt_counts,
                                 int max_pts, float *next_pts, uint8_t *status, float *err, int32_t *iters,
@@ -1168,26 +1086,19 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     if (max_pts == 0) return LKF_OK;
     LKLevels lv;
     const int B = prev_pyr[0].batch;
+    {
+        const int rc0 = lk_check_pyramids(prev_pyr, next_pyr, n_levels);
+        if (rc0 != LKF_OK) return rc0;
+    }
     for (int l = 0; l < n_levels; l++) {
-        if (!img_ok(&prev_pyr[l], 1, 1) || !img_ok(&next_pyr[l], 1, 1)) return LKF_ERR_ARG;
-        if (prev_pyr[l].batch != B || next_pyr[l].batch != B || prev_pyr[l].height != next_pyr[l].height ||
-            prev_pyr[l].width != next_pyr[l].width)
-            return LKF_ERR_ARG;
-        if (l > 0 && (prev_pyr[l].height != (prev_pyr[l - 1].height + 1) / 2 ||
-                      prev_pyr[l].width != (prev_pyr[l - 1].width + 1) / 2))
-            return LKF_ERR_ARG;
         lv.prev[l] = (const uint8_t *)prev_pyr[l].data; lv.next[l] = (const uint8_t *)next_pyr[l].data;
         lv.prp[l] = prev_pyr[l].row_pitch; lv.pip[l] = prev_pyr[l].image_pitch;
         lv.nrp[l] = next_pyr[l].row_pitch; lv.nip[l] = next_pyr[l].image_pitch;
         lv.H[l] = prev_pyr[l].height; lv.W[l] = prev_pyr[l].width;
     }
-    int max_count = p->max_count;
-    double eps = p->epsilon;
-    if (!(p->crit_type & LKF_TERM_CRITERIA_COUNT)) max_count = 30;
-    else max_count = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
-    if (!(p->crit_type & LKF_TERM_CRITERIA_EPS)) eps = 0.01;
-    else eps = eps < 0 ? 0 : (eps > 10 ? 10 : eps);
-    eps *= eps;
+    int max_count;
+    double eps;
+    lk_resolve_criteria(p, &max_count, &eps);
     const size_t pw = lk_per_warp_bytes(p->win_w, p->win_h);
     const size_t smem = pw * LK_WARPS;
     if (smem > 227 * 1024) return LKF_ERR_UNSUPPORTED;
@@ -1199,6 +1110,20 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
         if (aligned_to(&next_pyr[l], 4)) al4_mask |= 1u << l;
         if (aligned_to(&prev_pyr[l], 4)) ial4_mask |= 1u << l;
     }
+    // One point per pixel of level 0 and a small window: prevPts may be the raster grid (dense flow, config C4).  A device
+    // flag decides without a host round trip: k_lk_dense runs when the points ARE the grid, k_lk_track_small otherwise
+    // (the other one returns at once), so the call stays capturable.
+    const int *grid_flag = nullptr;
+    if (ctx && !pt_counts && (long long)max_pts == (long long)lv.W[0] * lv.H[0] && lk_dense_supported(p, n_levels)) {
+        void *fl;
+        int rcf = lkf_scratch(ctx, 5, 256, &fl, s);
+        if (rcf != LKF_OK) return rcf;
+        if ((rcf = lk_dense_grid_check(prev_pts, B, lv.W[0], lv.H[0], (int *)fl, s)) != LKF_OK) return rcf;
+        if ((rcf = lk_dense_launch(p, n_levels, prev_pyr, next_pyr, max_count, eps, next_pts, status, err, iters, (const int *)fl, s)) != LKF_OK)
+            return rcf;
+        lkf_count_launch(ctx); lkf_count_launch(ctx);
+        grid_flag = (const int *)fl;
+    }
     int rc = 1;
     if (p->win_w == 21 && p->win_h == 21)
         rc = launch_lk_t<21, 21, 7, 1, 22, 28, 28>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
@@ -1207,11 +1132,11 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     else if (p->win_w == 31 && p->win_h == 31)
         rc = launch_lk_t<31, 31, 31, 1, 33, 44, 16>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
     else if (p->win_w == 5 && p->win_h == 5)
-        rc = launch_lk_small<5, 5>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_small<5, 5>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s, grid_flag);
     else if (p->win_w == 3 && p->win_h == 3)
-        rc = launch_lk_small<3, 3>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_small<3, 3>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s, grid_flag);
     else if (p->win_w == 7 && p->win_h == 7)
-        rc = launch_lk_small<7, 7>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_small<7, 7>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s, grid_flag);
     if (rc < 0) return rc;
     if (rc == LKF_OK) { LKF_LAUNCH_CHECK(ctx); return LKF_OK; }
     if (area <= 2048) {      // int32 lane partials cannot overflow (<= 64 px/lane * 8160*4080)

@@ -138,6 +138,28 @@ def pyrlk(prev_pyr, next_pyr, pts, params, counts=None, next_pts=None, want_iter
     return (nxt, st, err, iters) if want_iters else (nxt, st, err)
 
 
+def pyrlk_dense(prev_pyr, next_pyr, params, want_iters=False, out=None):
+    """a7 for prevPts = every pixel of level 0 in raster order (config C4): -> (next_pts [B,H*W,2], status [B,H*W] u8,
+    err [B,H*W] f32[, iters]); same values as pyrlk() on that grid, no point array."""
+    ws = Workspace.current()
+    n_levels = len(prev_pyr)
+    B, H, W = prev_pyr[0].shape
+    dev = prev_pyr[0].device
+    if out is not None:
+        nxt, st, err = out
+    else:
+        nxt = torch.empty((B, H * W, 2), dtype=torch.float32, device=dev)
+        st = torch.empty((B, H * W), dtype=torch.uint8, device=dev)
+        err = torch.empty((B, H * W), dtype=torch.float32, device=dev)
+    iters = torch.zeros((B, H * W), dtype=torch.int32, device=dev) if want_iters else None
+    Arr = LkfImage * n_levels
+    pa = Arr(*[image_desc(t) for t in prev_pyr])
+    na = Arr(*[image_desc(t) for t in next_pyr])
+    check(ws.lib.lkf_pyrlk_dense(ws.ctx, ctypes.byref(params), n_levels, pa, na, nxt.data_ptr(), st.data_ptr(), err.data_ptr(),
+                                 None if iters is None else iters.data_ptr(), stream_ptr()), "lkf_pyrlk_dense")
+    return (nxt, st, err, iters) if want_iters else (nxt, st, err)
+
+
 def min_eigen(gray, block_size=3, dy_tail_cols=-1, out=None):
     """a5: cv.cornerMinEigenVal(img, blockSize, ksize=3) as goodFeaturesToTrack computes it."""
     ws = Workspace.current()

@@ -81,9 +81,16 @@ def c4():
     params = ops.lk_params_struct(**lk)
     res = ops.pyrlk(prev, nxt, pts, params, want_iters=True)
     it = float(res[3].float().mean().item())
-    ms = gpu_time(lambda: ops.pyrlk(prev, nxt, pts, params), reps=5)
+    ms = gpu_time(lambda: ops.pyrlk(prev, nxt, pts, params), reps=5)          # grid detected on the device -> k_lk_dense
+    buf = ops.pyrlk_dense(prev, nxt, params)
+    ms_dense = gpu_time(lambda: ops.pyrlk_dense(prev, nxt, params, out=buf), reps=5)
+    rev = pts.flip(1).contiguous()                                             # not the raster grid -> k_lk_track_small
+    ms_small = gpu_time(lambda: ops.pyrlk(prev, nxt, rev, params), reps=3)
+    one = ops.lk_params_struct(winSize=(5, 5), maxLevel=2, criteria=(1, 1, 0.0))
+    ms_one = gpu_time(lambda: ops.pyrlk_dense(prev, nxt, one, out=buf), reps=5)
     out = {"config": "C4 dense 1920x1080, 5x5, 3 levels, criteria (EPS|COUNT,10,0.03)", "features": W * H,
-           "gpu_ms": ms, "gpu_ns_per_feature": 1e6 * ms / (W * H), "iterations_per_feature": it,
+           "gpu_ms": ms, "gpu_ms_dense_entry": ms_dense, "gpu_ms_thread_per_feature_kernel": ms_small,
+           "gpu_ms_one_iteration_variant": ms_one, "gpu_ns_per_feature": 1e6 * ms / (W * H), "iterations_per_feature": it,
            "status_ok_share": float(res[1].float().mean().item())}
     # op model of SURVEY 8d: w h (27 L + 12 it + 9)
     out["gop"] = W * H * 25 * (27 * nl + 12 * it + 9) / 1e9
