@@ -480,25 +480,30 @@ k_nms_compact(const float *__restrict__ eig, long long erp, long long eip, int H
 
 // Same selection, 4 pixels per thread (128-bit loads of the centre row; rows above / below only where a pixel survives the
 // weakest threshold).  Needs 16-byte aligned eig rows.  Candidate order inside a list is irrelevant (sorted afterwards).
+// The candidates of a CTA (128 x 32 pixels) are counted in shared memory and appended with ONE global atomicAdd per list
+// (one per warp and row cost 47 % of the kernel's stall samples: ~30 000 same-address atomics per list).
 constexpr int NMS4_ROWS = 4;        // rows per thread (their centre loads are issued together: memory-level parallelism)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int H, int W, MaskSet ms, int n_masks,
                const unsigned *__restrict__ maxkey, double quality, unsigned long long *__restrict__ keys,
                int *__restrict__ counts, int cap, const int32_t *__restrict__ enable, int *__restrict__ hist)
 {
+    __shared__ int s_cnt[MAXM], s_base[MAXM];
     const int b = blockIdx.z;
     if (enable && !enable[b]) return;
     const int lane = threadIdx.x & 31;
     const int x0 = (blockIdx.x * 32 + lane) * 4;
     const int ybase = 1 + blockIdx.y * (8 * NMS4_ROWS) + (threadIdx.x >> 5);
     const unsigned char *e = reinterpret_cast<const unsigned char *>(eig) + (long long)b * eip;
+    if (threadIdx.x < MAXM) s_cnt[threadIdx.x] = 0;
     float thr_m[MAXM], thr_min = 3.4e38f;
+    unsigned mk[MAXM];
 #pragma unroll
     for (int m = 0; m < MAXM; m++) {
         if (m >= n_masks) break;
-        const unsigned mk = maxkey[b * n_masks + m];
-        thr_m[m] = (float)((mk ? (double)key2f(mk) : 0.0) * quality);
+        mk[m] = maxkey[b * n_masks + m];
+        thr_m[m] = (float)((mk[m] ? (double)key2f(mk[m]) : 0.0) * quality);
         thr_min = fminf(thr_min, thr_m[m]);
     }
     const bool full = x0 + 3 < W;
@@ -509,23 +514,24 @@ k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int 
         cq[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y < H - 1 && full) cq[r] = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(e + (long long)y * erp) + x0);
     }
+    unsigned mx = 0;                     // bit 4 r + j: pixel (x0 + j, ybase + 8 r) is a local maximum above the weakest threshold
 #pragma unroll
     for (int r = 0; r < NMS4_ROWS; r++) {
         const int y = ybase + 8 * r;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        bool is_max[4] = {false, false, false, false};
         if (y < H - 1 && x0 < W) {
             const float *r1 = reinterpret_cast<const float *>(e + (long long)y * erp) + x0;
             float c[6];                                     // columns x0-1 .. x0+4 of the centre row
-            if (full) { c[1] = cq[r].x; c[2] = cq[r].y; c[3] = cq[r].z; c[4] = cq[r].w; }
-            else
-                for (int j = 0; j < 4; j++) c[1 + j] = x0 + j < W ? r1[j] : 0.f;
+            if (!full) {
+                float t[4];
+                for (int j = 0; j < 4; j++) t[j] = x0 + j < W ? r1[j] : 0.f;
+                cq[r] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            c[1] = cq[r].x; c[2] = cq[r].y; c[3] = cq[r].z; c[4] = cq[r].w;
             bool any = false;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int x = x0 + j;
-                v[j] = c[1 + j];
-                any |= x >= 1 && x < W - 1 && v[j] > thr_min && v[j] != 0.f;
+                any |= x >= 1 && x < W - 1 && c[1 + j] > thr_min && c[1 + j] != 0.f;
             }
             if (any) {
                 const float *r0 = reinterpret_cast<const float *>(e + (long long)(y - 1) * erp) + x0;
@@ -542,37 +548,59 @@ k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int 
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int x = x0 + j;
-                    if (x >= 1 && x < W - 1 && v[j] > thr_min && v[j] != 0.f) {
+                    const float v = c[1 + j];
+                    if (x >= 1 && x < W - 1 && v > thr_min && v != 0.f) {
                         const float m = fmaxf(fmaxf(fmaxf(a[j], a[j + 1]), fmaxf(a[j + 2], c[j])), fmaxf(fmaxf(c[j + 2], d[j]), fmaxf(d[j + 1], d[j + 2])));
-                        is_max[j] = v[j] >= m;
+                        if (v >= m) mx |= 1u << (4 * r + j);
                     }
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, is_max[0] || is_max[1] || is_max[2] || is_max[3])) continue;
+    }
+    if (!__syncthreads_or(mx != 0)) return;               // (also orders the zeroing of s_cnt)
+    auto value = [&](int bit) -> float {
+        const float4 q = cq[bit >> 2];
+        const int j = bit & 3;
+        return j == 0 ? q.x : (j == 1 ? q.y : (j == 2 ? q.z : q.w));
+    };
+    // per list: the pixels that pass its threshold and mask; slots inside the CTA's block of the list
+    unsigned cb[MAXM];
+    int ofs[MAXM];
 #pragma unroll
-        for (int m = 0; m < MAXM; m++) {
-            if (m >= n_masks) break;
-            const int list = b * n_masks + m;
-            const float thr = thr_m[m];
+    for (int m = 0; m < MAXM; m++) {
+        if (m >= n_masks) break;
+        cb[m] = 0; ofs[m] = 0;
+        const int list = b * n_masks + m;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int x = x0 + j;
-                bool cand = is_max[j] && v[j] > thr;
-                if (cand && ms.p) cand = ms.p[(long long)(ms.per_image ? list : m) * ms.ip + (long long)y * ms.rp + x] != 0;
-                const unsigned bal = __ballot_sync(0xffffffffu, cand);
-                if (bal) {
-                    const int leader = __ffs(bal) - 1;
-                    int base = 0;
-                    if (lane == leader) base = atomicAdd(&counts[list], __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    if (cand) {
-                        const int pos = base + __popc(bal & ((1u << lane) - 1));
-                        if (pos < cap) keys[(long long)list * cap + pos] = ((unsigned long long)f2key(v[j]) << 32) | (unsigned)(y * W + x);
-                        atomicAdd(&hist[list * GF_BINS + key_bin(maxkey[list], f2key(v[j]))], 1);
-                    }
-                }
+        for (int bit = 0; bit < 4 * NMS4_ROWS; bit++) {
+            if (!((mx >> bit) & 1u)) continue;
+            bool cand = value(bit) > thr_m[m];
+            if (cand && ms.p) {
+                const int y = ybase + 8 * (bit >> 2), x = x0 + (bit & 3);
+                cand = ms.p[(long long)(ms.per_image ? list : m) * ms.ip + (long long)y * ms.rp + x] != 0;
             }
+            if (cand) cb[m] |= 1u << bit;
+        }
+        if (cb[m]) ofs[m] = atomicAdd(&s_cnt[m], __popc(cb[m]));
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < n_masks && s_cnt[threadIdx.x] > 0)
+        s_base[threadIdx.x] = atomicAdd(&counts[b * n_masks + threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MAXM; m++) {
+        if (m >= n_masks) break;
+        if (!cb[m]) continue;
+        const int list = b * n_masks + m;
+        int pos = s_base[m] + ofs[m];
+#pragma unroll
+        for (int bit = 0; bit < 4 * NMS4_ROWS; bit++) {
+            if (!((cb[m] >> bit) & 1u)) continue;
+            const int y = ybase + 8 * (bit >> 2), x = x0 + (bit & 3);
+            const unsigned k = f2key(value(bit));
+            if (pos < cap) keys[(long long)list * cap + pos] = ((unsigned long long)k << 32) | (unsigned)(y * W + x);
+            atomicAdd(&hist[list * GF_BINS + key_bin(mk[m], k)], 1);
+            pos++;
         }
     }
 }
@@ -591,7 +619,7 @@ k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int 
 // two such cells away, so "any accepted corner within minDistance" is the same predicate.)
 constexpr int SS_NT = 1024;
 constexpr int SS_SMEM_KEYS = 8192;
-constexpr int SS_MAX_CELLS = 24 * 1024;           // uint32 heads in shared memory (96 KB)
+constexpr int SS_MAX_CELLS = 16 * 1024;           // uint32 heads in shared memory (64 KB)
 constexpr unsigned SS_NIL = 0xffffffffu;
 
 __global__ void __launch_bounds__(SS_NT)
@@ -599,13 +627,14 @@ k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__
               int max_corners, double min_distance, int cs, int gw, int gh, unsigned *__restrict__ gnext_all,
               unsigned char *__restrict__ gstate_all, float *__restrict__ corners, int32_t *__restrict__ out_counts,
               int max_out, const int32_t *__restrict__ enable, int n_masks, const unsigned *__restrict__ maxkey,
-              const int *__restrict__ hist_all, unsigned long long *__restrict__ gtop_all)
+              const int *__restrict__ hist_all, unsigned long long *__restrict__ gtop_all, const int *__restrict__ done)
 {
     extern __shared__ __align__(16) unsigned char ss_smem[];
     __shared__ int s_scan[SS_NT / 32];
     __shared__ int s_base, s_cut, s_ntop, s_cnt;
     const int list = blockIdx.x, tid = threadIdx.x;
     if (enable && !enable[list / n_masks]) return;
+    if (done && done[list]) return;                        // k_sort_select_fast has written this list
     unsigned long long *gkeys = keys_all + (long long)list * cap;
     const int n_all = counts[list];
     const bool overflow = n_all > cap;
@@ -769,6 +798,269 @@ k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast selection path (the common case: maxCorners given, at most FS_MAX_N candidates to rank).
+//   k_top_filter (many CTAs per list): the strongest candidates -- histogram bins 0..cut, cut chosen so that at least
+//     `need` = 1.5 maxCorners + 256 candidates are kept -- are copied to a dense array; a CTA appends its matches with one
+//     global atomicAdd.  (One CTA per list streaming 60 000 keys was a third of the old kernel's time.)
+//   k_sort_select_fast (one CTA per list): RANKS the kept candidates instead of sorting them with a bitonic network:
+//     counting sort by histogram bin (the bin prefix is known from the histogram), then the exact rank inside a bin by
+//     counting the larger keys of that bin (bins hold a handful of candidates; a guard sends skewed lists to the general
+//     kernel).  Keys are unique (the raster index is part of the key), so ranks are a permutation.  Only the coordinates
+//     are written, in rank order; the key array's space then holds the neighbour grid.  The greedy min-distance pass and
+//     the output are those of k_sort_select.  Lists this kernel cannot finish (overflow, too many candidates, a skewed
+//     bin, or fewer than maxCorners corners among the kept candidates) are left to k_sort_select (done[list] stays 0).
+// ---------------------------------------------------------------------------------------------
+constexpr int FS_MAX_N = 16384, FS_MAX_BIN = 768;
+constexpr int TF_NT = 256, TF_PER_THREAD = 8, TF_CHUNK = TF_NT * TF_PER_THREAD, TF_CTAS = 32;
+
+__device__ __forceinline__ int gftt_need(int stop_at) { return stop_at + stop_at / 2 + 256; }
+
+// Smallest histogram bin `cut` with hist[0..cut] >= need (bins counted from the list's maximum downwards) and that count;
+// NT threads, GF_BINS / NT consecutive bins per thread.  Optionally stores the exclusive prefix of every bin and the largest
+// bin count among bins 0..cut.  s_out = {cut, n_top, max_bin}; cut = -1 if the whole histogram holds fewer than `need`.
+template <int NT>
+__device__ void find_cut(const int *__restrict__ hist, int need, int *s_scan, int *s_out, int *prefix)
+{
+    constexpr int PER = GF_BINS / NT;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int h[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { h[i] = hist[PER * tid + i]; sum += h[i]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (tid == 0) { s_out[0] = -1; s_out[1] = 0; s_out[2] = 0; }
+    if (lane == 31) s_scan[wid] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; w++) woff += s_scan[w];
+    int run = incl + woff - sum;                           // exclusive prefix of this thread's first bin
+    int cut = -1, ntop = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        if (prefix) prefix[PER * tid + i] = run;
+        if (run < need && need <= run + h[i]) { cut = PER * tid + i; ntop = run + h[i]; }
+        run += h[i];
+    }
+    if (cut >= 0) { s_out[0] = cut; s_out[1] = ntop; }
+    __syncthreads();
+    {
+        const int c = s_out[0];
+        int mb = 0;
+#pragma unroll
+        for (int i = 0; i < PER; i++) if (c < 0 || PER * tid + i <= c) mb = max(mb, h[i]);
+        mb = __reduce_max_sync(0xffffffffu, mb);
+        if (lane == 0 && mb > 0) atomicMax(&s_out[2], mb);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TF_NT)
+k_top_filter(const unsigned long long *__restrict__ keys_all, const int *__restrict__ counts, int cap, int max_corners, int max_out,
+             const int32_t *__restrict__ enable, int n_masks, const unsigned *__restrict__ maxkey, const int *__restrict__ hist_all,
+             unsigned long long *__restrict__ gtop_all, int *__restrict__ top_count)
+{
+    __shared__ int s_scan[TF_NT / 32], s_out[3], s_n, s_base;
+    const int list = blockIdx.y, tid = threadIdx.x;
+    if (enable && !enable[list / n_masks]) return;
+    const int n_full = counts[list];
+    if (n_full > cap) return;
+    if (!(max_corners > 0 && max_corners <= max_out)) return;
+    const int need = gftt_need(max_corners);
+    if (!(n_full > need + need / 4)) return;
+    find_cut<TF_NT>(hist_all + list * GF_BINS, need, s_scan, s_out, nullptr);
+    const int cut = s_out[0];
+    if (cut < 0) return;
+    const unsigned kmax = maxkey[list];
+    const unsigned long long *gk = keys_all + (long long)list * cap;
+    unsigned long long *gt = gtop_all + (long long)list * cap;
+    for (int blk = blockIdx.x; (long long)blk * TF_CHUNK < n_full; blk += gridDim.x) {
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        unsigned long long k[TF_PER_THREAD];
+        unsigned hit = 0;
+#pragma unroll
+        for (int j = 0; j < TF_PER_THREAD; j++) {
+            const int i = blk * TF_CHUNK + j * TF_NT + tid;
+            k[j] = i < n_full ? gk[i] : 0ull;
+            if (i < n_full && key_bin(kmax, (unsigned)(k[j] >> 32)) <= cut) hit |= 1u << j;
+        }
+        int ofs = 0;
+        if (hit) ofs = atomicAdd(&s_n, __popc(hit));
+        __syncthreads();
+        if (tid == 0 && s_n) s_base = atomicAdd(&top_count[list], s_n);
+        __syncthreads();
+        if (hit) {
+            int pos = s_base + ofs;
+#pragma unroll
+            for (int j = 0; j < TF_PER_THREAD; j++)
+                if ((hit >> j) & 1u) gt[pos++] = k[j];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SS_NT)
+k_sort_select_fast(const unsigned long long *__restrict__ keys_all, const int *__restrict__ counts, int cap, int W, int H,
+                   int max_corners, double min_distance, int cs, int gw, int gh, float *__restrict__ corners,
+                   int32_t *__restrict__ out_counts, int max_out, const int32_t *__restrict__ enable, int n_masks,
+                   const unsigned *__restrict__ maxkey, const int *__restrict__ hist_all,
+                   const unsigned long long *__restrict__ gtop_all, const int *__restrict__ top_count, int *__restrict__ done)
+{
+    extern __shared__ __align__(16) unsigned char fs_smem[];
+    __shared__ int s_scan[SS_NT / 32], s_out[3], s_base;
+    unsigned long long *A = reinterpret_cast<unsigned long long *>(fs_smem);                 // FS_MAX_N keys (bin order)
+    unsigned *xy = reinterpret_cast<unsigned *>(fs_smem + (size_t)FS_MAX_N * 8);             // FS_MAX_N coordinates (rank order)
+    int *prefix = reinterpret_cast<int *>(fs_smem + (size_t)FS_MAX_N * 12);                  // GF_BINS
+    int *fill = prefix + GF_BINS;                                                            // GF_BINS
+    // after ranking: the neighbour grid lives in A's space, the states in prefix/fill's
+    unsigned *heads = reinterpret_cast<unsigned *>(fs_smem);                                 // <= SS_MAX_CELLS
+    unsigned *nxt = heads + SS_MAX_CELLS;                                                    // FS_MAX_N
+    volatile unsigned char *state = reinterpret_cast<volatile unsigned char *>(prefix);     // FS_MAX_N
+    static_assert(SS_MAX_CELLS * 4 + FS_MAX_N * 4 <= FS_MAX_N * 8 && FS_MAX_N <= 2 * GF_BINS * 4, "overlay sizes");
+
+    const int list = blockIdx.x, tid = threadIdx.x;
+    if (enable && !enable[list / n_masks]) return;
+    const int n_full = counts[list];
+    if (n_full > cap) return;                                                                // overflow: general kernel
+    const int stop_at = (max_corners > 0 && max_corners <= max_out) ? max_corners : 0x7fffffff;
+    const int *hist = hist_all + list * GF_BINS;
+    const unsigned kmax = maxkey ? maxkey[list] : 0u;
+    bool trunc = false;
+    int need = 0x7fffffff;
+    if (stop_at != 0x7fffffff) {
+        need = gftt_need(stop_at);
+        trunc = n_full > need + need / 4;
+    }
+    find_cut<SS_NT>(hist, trunc ? need : 0x7fffffff, s_scan, s_out, prefix);
+    fill[2 * tid] = 0; fill[2 * tid + 1] = 0;
+    int n = n_full;
+    const unsigned long long *src = keys_all + (long long)list * cap;
+    if (trunc) {
+        if (s_out[0] < 0) return;
+        n = s_out[1];
+        src = gtop_all + (long long)list * cap;
+        if (top_count[list] != n) return;                                                    // (cannot happen; keeps the fallback safe)
+    }
+    if (n > FS_MAX_N || s_out[2] > FS_MAX_BIN) return;                                       // block-uniform
+    __syncthreads();
+    // counting sort by bin
+    for (int i = tid; i < n; i += SS_NT) {
+        const unsigned long long k = src[i];
+        const int bin = key_bin(kmax, (unsigned)(k >> 32));
+        A[prefix[bin] + atomicAdd(&fill[bin], 1)] = k;
+    }
+    __syncthreads();
+    // exact rank inside the bin; coordinates in rank order
+    for (int i = tid; i < n; i += SS_NT) {
+        const unsigned long long k = A[i];
+        const int bin = key_bin(kmax, (unsigned)(k >> 32));
+        const int start = prefix[bin], end = start + fill[bin];
+        int rank = start;
+        for (int j = start; j < end; j++) rank += A[j] > k ? 1 : 0;
+        const unsigned idx = (unsigned)k;
+        const unsigned y = idx / (unsigned)W, x = idx - y * (unsigned)W;
+        xy[rank] = (y << 16) | x;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += SS_NT) state[i] = (min_distance >= 1) ? 0 : 1;
+    int accepted = n;
+    if (min_distance >= 1) {
+        for (int i = tid; i < gw * gh; i += SS_NT) heads[i] = SS_NIL;
+        __syncthreads();
+        for (int i = tid; i < n; i += SS_NT) {
+            const unsigned v = xy[i];
+            const int cell = ((v >> 16) / cs) * gw + (v & 0xffff) / cs;
+            nxt[i] = atomicExch(&heads[cell], (unsigned)i);
+        }
+        __syncthreads();
+        const float md2 = (float)(min_distance * min_distance);     // integer coordinates: d2 is exact
+        const bool md2_exact = (double)md2 == min_distance * min_distance;
+        accepted = 0;
+        for (int base = 0; base < n && accepted < stop_at; base += SS_NT) {
+            const int i = base + tid;
+            // higher-ranked candidates closer than minDistance: found once (first round), re-checked from registers
+            int nb[4], n_nb = -1;
+            for (;;) {
+                int pending = 0;
+                if (i < n && !state[i]) {
+                    int verdict = 1;
+                    if (n_nb < 0 || n_nb > 4) {
+                        const unsigned v = xy[i];
+                        const int x = v & 0xffff, y = v >> 16;
+                        const int cx = x / cs, cy = y / cs;
+                        int cntn = 0;
+                        for (int yy = max(0, cy - 1); yy <= min(gh - 1, cy + 1); yy++)
+                            for (int xx = max(0, cx - 1); xx <= min(gw - 1, cx + 1); xx++)
+                                for (unsigned j = heads[yy * gw + xx]; j != SS_NIL; j = nxt[j]) {
+                                    if ((int)j >= i) continue;
+                                    const unsigned u = xy[j];
+                                    const float dx = (float)(x - (int)(u & 0xffff)), dy = (float)(y - (int)(u >> 16));
+                                    const float d2 = dx * dx + dy * dy;
+                                    const bool close = md2_exact ? (d2 < md2) : ((double)d2 < min_distance * min_distance);
+                                    if (close) {
+                                        if (cntn < 4) nb[cntn] = (int)j;
+                                        cntn++;
+                                        const unsigned sj = state[j];
+                                        if (sj == 1) verdict = 2;
+                                        else if (sj == 0 && verdict != 2) verdict = 0;
+                                    }
+                                }
+                        n_nb = cntn;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (q < n_nb) {
+                                const unsigned sj = state[nb[q]];
+                                if (sj == 1) verdict = 2;
+                                else if (sj == 0 && verdict != 2) verdict = 0;
+                            }
+                    }
+                    if (verdict) state[i] = (unsigned char)verdict; else pending = 1;
+                }
+                if (!__syncthreads_or(pending)) break;
+            }
+            accepted += __syncthreads_count(i < n && state[i] == 1);
+        }
+    }
+    if (trunc && accepted < stop_at) return;                  // the kept candidates do not suffice: general kernel, full list
+    __syncthreads();
+    // rank-ordered compaction of the accepted candidates, cut at `limit`
+    float *out = corners + (size_t)list * max_out * 2;
+    const int limit = (max_corners > 0 && max_corners < max_out) ? max_corners : max_out;
+    const bool may_truncate = max_corners <= 0 || max_corners > max_out;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += SS_NT) {
+        const int i = base + tid;
+        const int acc = (i < n && state[i] == 1) ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, acc);
+        const int lane = tid & 31, wid = tid >> 5;
+        if (lane == 0) s_scan[wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int w = 0; w < SS_NT / 32; w++) { const int c = s_scan[w]; if (w < wid) woff += c; total += c; }
+        const int pos = s_base + woff + __popc(bal & ((1u << lane) - 1));
+        if (acc && pos < limit) {
+            const unsigned v = xy[i];
+            out[2 * pos] = (float)(v & 0xffff); out[2 * pos + 1] = (float)(v >> 16);
+        }
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
+        if (s_base >= limit && !may_truncate) break;
+    }
+    if (tid == 0) {
+        const int total = s_base;
+        const int nc = total < limit ? total : limit;
+        const bool truncated = may_truncate && total > limit;
+        out_counts[list] = truncated ? -1 - nc : nc;
+        done[list] = 1;
+    }
+}
+
 }  // namespace
 
 static int make_mask_set(const lkf_image *mask, int n_masks, int B, int H, int W, MaskSet *out)
@@ -830,7 +1122,7 @@ LKF_EXPORT int lkf_corner_min_eigen_f32(const lkf_image *src, const lkf_image *e
 }
 
 struct GfttScratch {
-    unsigned long long *keys, *top; unsigned *maxkey; int *ccount, *hist; void *gaux;
+    unsigned long long *keys, *top; unsigned *maxkey; int *ccount, *hist, *topcount, *done; void *gaux;
     int cap, cs, gw, gh, lists;
 };
 
@@ -859,7 +1151,7 @@ static int gftt_prepare(lkf_ctx *ctx, const lkf_gftt_params *p, int B, int H, in
     }
     void *keys, *cnt, *top;
     int rc;
-    const size_t cnt_ints = (size_t)g->lists * (2 + GF_BINS);
+    const size_t cnt_ints = (size_t)g->lists * (4 + GF_BINS);
     if ((rc = lkf_scratch(ctx, 0, (size_t)g->lists * g->cap * 8, &keys, (cudaStream_t)stream)) != LKF_OK) return rc;
     if ((rc = lkf_scratch(ctx, 1, cnt_ints * sizeof(int), &cnt, (cudaStream_t)stream)) != LKF_OK) return rc;
     if ((rc = lkf_scratch(ctx, 2, (size_t)g->lists * g->cap * 5, &g->gaux, (cudaStream_t)stream)) != LKF_OK) return rc;     // next (u32) + state (u8), large lists only
@@ -868,7 +1160,9 @@ static int gftt_prepare(lkf_ctx *ctx, const lkf_gftt_params *p, int B, int H, in
     g->top = (unsigned long long *)top;
     g->maxkey = (unsigned *)cnt;
     g->ccount = (int *)cnt + g->lists;
-    g->hist = (int *)cnt + 2 * g->lists;
+    g->topcount = (int *)cnt + 2 * g->lists;
+    g->done = (int *)cnt + 3 * g->lists;
+    g->hist = (int *)cnt + 4 * g->lists;
     LKF_CUDA(cudaMemsetAsync(cnt, 0, cnt_ints * sizeof(int), (cudaStream_t)stream));
     return LKF_OK;
 }
@@ -896,10 +1190,22 @@ static int gftt_passes(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *
     }
     LKF_LAUNCH_CHECK(ctx);
     const size_t ss_smem = (size_t)SS_SMEM_KEYS * 8 + (size_t)SS_MAX_CELLS * 4 + (size_t)SS_SMEM_KEYS * 4 + SS_SMEM_KEYS;
-    LKF_FUNC_ATTRS(LKF_CUDA(cudaFuncSetAttribute(k_sort_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_smem)));
+    const size_t fs_smem = (size_t)FS_MAX_N * 12 + (size_t)GF_BINS * 8;
+    LKF_FUNC_ATTRS({
+        LKF_CUDA(cudaFuncSetAttribute(k_sort_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_smem));
+        LKF_CUDA(cudaFuncSetAttribute(k_sort_select_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs_smem));
+    });
+    k_top_filter<<<dim3(TF_CTAS, g.lists), TF_NT, 0, s>>>(g.keys, g.ccount, g.cap, p->max_corners, max_out, enable, n_masks, g.maxkey,
+                                                         g.hist, g.top, g.topcount);
+    LKF_LAUNCH_CHECK(ctx);
+    k_sort_select_fast<<<g.lists, SS_NT, fs_smem, s>>>(g.keys, g.ccount, g.cap, W, H, p->max_corners, p->min_distance, g.cs, g.gw, g.gh,
+                                                      corners, counts, max_out, enable, n_masks, g.maxkey, g.hist, g.top, g.topcount,
+                                                      g.done);
+    LKF_LAUNCH_CHECK(ctx);
+    // whatever the fast kernel left (done[list] == 0): capacity overflow, unlimited or very long lists, skewed bins
     k_sort_select<<<g.lists, SS_NT, ss_smem, s>>>(g.keys, g.ccount, g.cap, W, H, p->max_corners, p->min_distance, g.cs, g.gw,
                                                  g.gh, (unsigned *)g.gaux, (unsigned char *)g.gaux + (size_t)g.lists * g.cap * 4, corners,
-                                                 counts, max_out, enable, n_masks, g.maxkey, g.hist, g.top);
+                                                 counts, max_out, enable, n_masks, g.maxkey, g.hist, g.top, g.done);
     LKF_LAUNCH_CHECK(ctx);
     return LKF_OK;
 }

@@ -15,13 +15,14 @@
 //   * mismatch vector of an iteration = sum J~ (Ix~, Iy~) - sum I~ (Ix~, Iy~); the second term is a per-level constant of
 //     the feature, so an iteration reads one packed gradient word per window pixel.
 #include "lk_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
-constexpr int DN_TW = 32, DN_TH = 8, DN_NT = DN_TW * DN_TH;      // features per CTA = threads per CTA
+constexpr int DN_TW = 32;      // tile width; tile height TH is a template parameter (features per CTA = threads per CTA = 32 TH)
 constexpr int DN_MAX_LEVELS = 4;
 
-template <int WIN>
+template <int WIN, int DN_TH>
 struct DN {
     static constexpr int R = (WIN - 1) / 2;
     static constexpr int halo(int l) { return R << l; }
@@ -38,6 +39,7 @@ struct DN {
 };
 
 // per-feature state of a tile (structure of arrays in shared memory)
+template <int DN_NT>
 struct DNState {
     float npx[DN_NT], npy[DN_NT];        // nextPts estimate at the current level (cv2's nextPts[ptidx] * 2 between levels)
     float nx[DN_NT], ny[DN_NT];          // iterate minus the half window
@@ -52,11 +54,11 @@ struct DNState {
     int n_next[3];
 };
 
-template <int WIN>
+template <int WIN, int DN_TH>
 size_t dn_smem_bytes(int n_levels)
 {
-    using D = DN<WIN>;
-    size_t b = sizeof(DNState);
+    using D = DN<WIN, DN_TH>;
+    size_t b = sizeof(DNState<DN_TW * DN_TH>);
     b = (b + 15) & ~(size_t)15;
     b += (size_t)D::map_elems(n_levels) * 8;              // mapD (int2: Ix~, Iy~)
     b += ((size_t)D::map_elems(n_levels) * 2 + 15) & ~(size_t)15;   // mapI
@@ -65,20 +67,21 @@ size_t dn_smem_bytes(int n_levels)
     return b;
 }
 
-template <int WIN>
-__global__ void __launch_bounds__(DN_NT, 4)
+template <int WIN, int DN_TH>
+__global__ void __launch_bounds__(DN_TW * DN_TH, 1024 / (DN_TW * DN_TH))
 k_lk_dense(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, double min_eig_thr,
            float *__restrict__ next_pts, uint8_t *__restrict__ status, float *__restrict__ err,
            int *__restrict__ iters_out, unsigned al4_mask, int map_elems, int sch_elems,
            const int *__restrict__ grid_flag)
 {
-    using D = DN<WIN>;
+    using D = DN<WIN, DN_TH>;
+    constexpr int DN_NT = DN_TW * DN_TH;
     constexpr int R = D::R, AREA = WIN * WIN, NWJ = (WIN + 1 + 3) / 4;
     static_assert(AREA <= 49, "exact int32 window sums");
     if (grid_flag && !*grid_flag) return;                 // prevPts is not the raster grid: the sparse kernel runs instead
     extern __shared__ __align__(16) unsigned char dn_smem[];
-    DNState &S = *reinterpret_cast<DNState *>(dn_smem);
-    int2 *mapD = reinterpret_cast<int2 *>(dn_smem + ((sizeof(DNState) + 15) & ~(size_t)15));
+    DNState<DN_NT> &S = *reinterpret_cast<DNState<DN_NT> *>(dn_smem);
+    int2 *mapD = reinterpret_cast<int2 *>(dn_smem + ((sizeof(DNState<DN_NT>) + 15) & ~(size_t)15));
     unsigned short *mapI = reinterpret_cast<unsigned short *>(mapD + map_elems);
     int *sch = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(mapI) + (((size_t)map_elems * 2 + 15) & ~(size_t)15));
     unsigned char *raw = reinterpret_cast<unsigned char *>(sch + sch_elems);
@@ -209,17 +212,33 @@ k_lk_dense(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, doub
 
         // (WIN+1) rows of (WIN+1) bytes of `next` at integer origin (ix, iy), packed from byte 0 of each row's words
         auto load_window = [&](int ix, int iy, uint32_t (&jr)[WIN + 1][NWJ]) {
-            const int ax = (ix >> 2) << 2;
-            if (jal4 && ax >= 0 && ax + 4 * (NWJ + 1) <= W && iy >= 0 && iy + WIN < H) {      // whole footprint inside the level
-                const uint32_t *q = reinterpret_cast<const uint32_t *>(J + (long long)iy * jrp + ax);
+            if (jal4 && ix >= 0 && ix + WIN + 1 <= W) {
+                // columns inside the level: aligned words (rows outside the level are mirrored).  The word holding the
+                // last byte lies inside the 4-byte aligned row pitch; a further word is read only if a byte of it is used.
+                const uint32_t *q0 = reinterpret_cast<const uint32_t *>(J + (long long)iy * jrp + ((ix >> 2) << 2));
                 const int sh = (ix & 3) * 8, rw = (int)(jrp >> 2);
+                const bool more = (ix & 3) + WIN + 1 > 4 * NWJ;
+                if (iy >= 0 && iy + WIN < H) {
 #pragma unroll
-                for (int y = 0; y <= WIN; y++) {
-                    uint32_t t[NWJ + 1];
+                    for (int y = 0; y <= WIN; y++) {
+                        uint32_t t[NWJ + 1];
 #pragma unroll
-                    for (int i = 0; i <= NWJ; i++) t[i] = __ldg(q + y * rw + i);
+                        for (int i = 0; i < NWJ; i++) t[i] = __ldg(q0 + y * rw + i);
+                        t[NWJ] = more ? __ldg(q0 + y * rw + NWJ) : 0u;
 #pragma unroll
-                    for (int i = 0; i < NWJ; i++) jr[y][i] = __funnelshift_r(t[i], t[i + 1], sh);
+                        for (int i = 0; i < NWJ; i++) jr[y][i] = __funnelshift_r(t[i], t[i + 1], sh);
+                    }
+                } else {
+#pragma unroll
+                    for (int y = 0; y <= WIN; y++) {
+                        const uint32_t *q = q0 + (reflect101(iy + y, H) - iy) * rw;
+                        uint32_t t[NWJ + 1];
+#pragma unroll
+                        for (int i = 0; i < NWJ; i++) t[i] = __ldg(q + i);
+                        t[NWJ] = more ? __ldg(q + NWJ) : 0u;
+#pragma unroll
+                        for (int i = 0; i < NWJ; i++) jr[y][i] = __funnelshift_r(t[i], t[i + 1], sh);
+                    }
                 }
             } else {
 #pragma unroll
@@ -357,19 +376,20 @@ k_grid_check(const float2 *__restrict__ pts, long long n_total, int W, long long
     if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) *flag = 0;
 }
 
-template <int WIN>
+template <int WIN, int DN_TH>
 int launch_dense(const LKLevels &lv, int n_levels, int max_count, double eps, const lkf_lk_params *p, float *next_pts, uint8_t *status,
                  float *err, int32_t *iters, unsigned al4_mask, int B, const int *grid_flag, cudaStream_t s)
 {
-    using D = DN<WIN>;
-    const size_t smem = dn_smem_bytes<WIN>(n_levels);
+    using D = DN<WIN, DN_TH>;
+    constexpr int DN_NT = DN_TW * DN_TH;
+    const size_t smem = dn_smem_bytes<WIN, DN_TH>(n_levels);
     if (smem > 227 * 1024) return LKF_ERR_UNSUPPORTED;
     LKF_FUNC_ATTRS({
-        LKF_CUDA(cudaFuncSetAttribute(k_lk_dense<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dn_smem_bytes<WIN>(DN_MAX_LEVELS)));
-        LKF_CUDA(cudaFuncSetAttribute(k_lk_dense<WIN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        LKF_CUDA(cudaFuncSetAttribute(k_lk_dense<WIN, DN_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dn_smem_bytes<WIN, DN_TH>(DN_MAX_LEVELS)));
+        LKF_CUDA(cudaFuncSetAttribute(k_lk_dense<WIN, DN_TH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     });
     dim3 grid((lv.W[0] + DN_TW - 1) / DN_TW, (lv.H[0] + DN_TH - 1) / DN_TH, B);
-    k_lk_dense<WIN><<<grid, DN_NT, smem, s>>>(lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, next_pts, status, err,
+    k_lk_dense<WIN, DN_TH><<<grid, DN_NT, smem, s>>>(lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, next_pts, status, err,
                                               iters, al4_mask, D::map_elems(n_levels), D::sch_elems(n_levels), grid_flag);
     return LKF_OK;
 }
@@ -408,10 +428,18 @@ int lk_dense_launch(const lkf_lk_params *p, int n_levels, const lkf_image *prev_
         lv.H[l] = prev_pyr[l].height; lv.W[l] = prev_pyr[l].width;
         if (aligned_to(&next_pyr[l], 4)) al4_mask |= 1u << l;
     }
+    static const int th = getenv("LKF_DN_TH") ? atoi(getenv("LKF_DN_TH")) : 8;      // tile height (tuning switch)
+    if (th == 4) {
+        switch (p->win_w) {
+        case 3: return launch_dense<3, 4>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
+        case 5: return launch_dense<5, 4>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
+        case 7: return launch_dense<7, 4>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
+        }
+    }
     switch (p->win_w) {
-    case 3: return launch_dense<3>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
-    case 5: return launch_dense<5>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
-    case 7: return launch_dense<7>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
+    case 3: return launch_dense<3, 8>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
+    case 5: return launch_dense<5, 8>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
+    case 7: return launch_dense<7, 8>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
     }
     return LKF_ERR_UNSUPPORTED;
 }
