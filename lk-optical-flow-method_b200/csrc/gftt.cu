@@ -813,6 +813,8 @@ k_sort_select(unsigned long long *__restrict__ keys_all, const int *__restrict__
 //     bin, or fewer than maxCorners corners among the kept candidates) are left to k_sort_select (done[list] stays 0).
 // ---------------------------------------------------------------------------------------------
 constexpr int FS_MAX_N = 16384, FS_MAX_BIN = 768;
+constexpr int FS_MAX_CELLS = 32 * 1024;           // uint16 heads (candidate ranks are < FS_MAX_N): a finer grid than SS_MAX_CELLS allows
+constexpr unsigned short FS_NIL = 0xffffu;
 constexpr int TF_NT = 256, TF_PER_THREAD = 8, TF_CHUNK = TF_NT * TF_PER_THREAD, TF_CTAS = 32;
 
 __device__ __forceinline__ int gftt_need(int stop_at) { return stop_at + stop_at / 2 + 256; }
@@ -916,10 +918,10 @@ k_sort_select_fast(const unsigned long long *__restrict__ keys_all, const int *_
     int *prefix = reinterpret_cast<int *>(fs_smem + (size_t)FS_MAX_N * 12);                  // GF_BINS
     int *fill = prefix + GF_BINS;                                                            // GF_BINS
     // after ranking: the neighbour grid lives in A's space, the states in prefix/fill's
-    unsigned *heads = reinterpret_cast<unsigned *>(fs_smem);                                 // <= SS_MAX_CELLS
-    unsigned *nxt = heads + SS_MAX_CELLS;                                                    // FS_MAX_N
+    unsigned short *heads = reinterpret_cast<unsigned short *>(fs_smem);                     // <= FS_MAX_CELLS
+    unsigned short *nxt = heads + FS_MAX_CELLS;                                              // FS_MAX_N
     volatile unsigned char *state = reinterpret_cast<volatile unsigned char *>(prefix);     // FS_MAX_N
-    static_assert(SS_MAX_CELLS * 4 + FS_MAX_N * 4 <= FS_MAX_N * 8 && FS_MAX_N <= 2 * GF_BINS * 4, "overlay sizes");
+    static_assert(FS_MAX_CELLS * 2 + FS_MAX_N * 2 <= FS_MAX_N * 8 && FS_MAX_N <= 2 * GF_BINS * 4 && FS_MAX_N < 0xffff, "overlay sizes");
 
     const int list = blockIdx.x, tid = threadIdx.x;
     if (enable && !enable[list / n_masks]) return;
@@ -968,16 +970,27 @@ k_sort_select_fast(const unsigned long long *__restrict__ keys_all, const int *_
     for (int i = tid; i < n; i += SS_NT) state[i] = (min_distance >= 1) ? 0 : 1;
     int accepted = n;
     if (min_distance >= 1) {
-        for (int i = tid; i < gw * gh; i += SS_NT) heads[i] = SS_NIL;
+        for (int i = tid; i < (gw * gh + 1) / 2; i += SS_NT) reinterpret_cast<unsigned *>(heads)[i] = 0xffffffffu;
         __syncthreads();
+        // Linked lists per cell, built by rank windows: inside a window the order of the 16-bit exchange emulation does not
+        // matter, a cell's list is only ever traversed completely.
         for (int i = tid; i < n; i += SS_NT) {
             const unsigned v = xy[i];
             const int cell = ((v >> 16) / cs) * gw + (v & 0xffff) / cs;
-            nxt[i] = atomicExch(&heads[cell], (unsigned)i);
+            // atomic exchange on a 16-bit slot: CAS loop on the containing word
+            unsigned *wp = reinterpret_cast<unsigned *>(heads) + (cell >> 1);
+            const int sh = (cell & 1) * 16;
+            unsigned old = *wp, assumed;
+            do {
+                assumed = old;
+                old = atomicCAS(wp, assumed, (assumed & ~(0xffffu << sh)) | ((unsigned)i << sh));
+            } while (old != assumed);
+            nxt[i] = (unsigned short)((old >> sh) & 0xffffu);
         }
         __syncthreads();
-        const float md2 = (float)(min_distance * min_distance);     // integer coordinates: d2 is exact
-        const bool md2_exact = (double)md2 == min_distance * min_distance;
+        // integer coordinates: d2 is an exact integer, "d2 < minDistance^2" is "d2 < ceil(minDistance^2)"
+        const double md2d = min_distance * min_distance;
+        const int ithr = md2d >= 2.0e9 ? 0x7fffffff : (int)ceil(md2d);
         accepted = 0;
         for (int base = 0; base < n && accepted < stop_at; base += SS_NT) {
             const int i = base + tid;
@@ -994,13 +1007,11 @@ k_sort_select_fast(const unsigned long long *__restrict__ keys_all, const int *_
                         int cntn = 0;
                         for (int yy = max(0, cy - 1); yy <= min(gh - 1, cy + 1); yy++)
                             for (int xx = max(0, cx - 1); xx <= min(gw - 1, cx + 1); xx++)
-                                for (unsigned j = heads[yy * gw + xx]; j != SS_NIL; j = nxt[j]) {
+                                for (unsigned j = heads[yy * gw + xx]; j != FS_NIL; j = nxt[j]) {
                                     if ((int)j >= i) continue;
                                     const unsigned u = xy[j];
-                                    const float dx = (float)(x - (int)(u & 0xffff)), dy = (float)(y - (int)(u >> 16));
-                                    const float d2 = dx * dx + dy * dy;
-                                    const bool close = md2_exact ? (d2 < md2) : ((double)d2 < min_distance * min_distance);
-                                    if (close) {
+                                    const int dx = x - (int)(u & 0xffff), dy = y - (int)(u >> 16);
+                                    if (dx * dx + dy * dy < ithr) {
                                         if (cntn < 4) nb[cntn] = (int)j;
                                         cntn++;
                                         const unsigned sj = state[j];
@@ -1124,6 +1135,7 @@ LKF_EXPORT int lkf_corner_min_eigen_f32(const lkf_image *src, const lkf_image *e
 struct GfttScratch {
     unsigned long long *keys, *top; unsigned *maxkey; int *ccount, *hist, *topcount, *done; void *gaux;
     int cap, cs, gw, gh, lists;
+    int fcs, fgw, fgh;          // neighbour grid of the fast selection kernel (finer: 16-bit heads)
 };
 
 // validates the selection arguments, sizes the scratch buffers and zeroes the per-list maxima / candidate counts
@@ -1147,6 +1159,15 @@ static int gftt_prepare(lkf_ctx *ctx, const lkf_gftt_params *p, int B, int H, in
             g->gw = (W + g->cs - 1) / g->cs; g->gh = (H + g->cs - 1) / g->cs;
             if ((long long)g->gw * g->gh <= SS_MAX_CELLS) break;
             g->cs++;
+        }
+    }
+    g->fcs = 1; g->fgw = 1; g->fgh = 1;
+    if (p->min_distance >= 1) {
+        g->fcs = (int)ceil(p->min_distance);
+        for (;;) {
+            g->fgw = (W + g->fcs - 1) / g->fcs; g->fgh = (H + g->fcs - 1) / g->fcs;
+            if ((long long)g->fgw * g->fgh <= FS_MAX_CELLS) break;
+            g->fcs++;
         }
     }
     void *keys, *cnt, *top;
@@ -1198,7 +1219,7 @@ static int gftt_passes(lkf_ctx *ctx, const lkf_gftt_params *p, const lkf_image *
     k_top_filter<<<dim3(TF_CTAS, g.lists), TF_NT, 0, s>>>(g.keys, g.ccount, g.cap, p->max_corners, max_out, enable, n_masks, g.maxkey,
                                                          g.hist, g.top, g.topcount);
     LKF_LAUNCH_CHECK(ctx);
-    k_sort_select_fast<<<g.lists, SS_NT, fs_smem, s>>>(g.keys, g.ccount, g.cap, W, H, p->max_corners, p->min_distance, g.cs, g.gw, g.gh,
+    k_sort_select_fast<<<g.lists, SS_NT, fs_smem, s>>>(g.keys, g.ccount, g.cap, W, H, p->max_corners, p->min_distance, g.fcs, g.fgw, g.fgh,
                                                       corners, counts, max_out, enable, n_masks, g.maxkey, g.hist, g.top, g.topcount,
                                                       g.done);
     LKF_LAUNCH_CHECK(ctx);

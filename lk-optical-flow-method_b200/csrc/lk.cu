@@ -12,6 +12,9 @@
 //      so they follow cv2's float32 sequence; only the (exact) integer sums replace cv2's float32
 //      lane accumulation (difference <= 3e-4 px, see tests).
 #include "lk_common.cuh"
+#include "tma.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -223,14 +226,21 @@ k_lk_track(LKLevels lv, int n_levels, int w, int h, int max_count, LKEps eps2, i
 // ---------------------------------------------------------------------------------------------
 constexpr int LKT_WARPS = 1;     // one feature per CTA: registers and shared memory are released the moment it converges
 
-template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_>
+// TMA = true: tile and template neighbourhood arrive by cp.async.bulk.tensor (3D boxes TWC x TH / RWP x RH of the level
+// planes): pitches are multiples of 16 bytes, buffers 128-byte aligned, three mbarriers follow the template patch.
+template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, bool TMA = false>
 struct LKT {
     static constexpr int AREA = WW * WH, WW_ = WW, WH_ = WH, RUN_ = RUN;
     static constexpr int RPR = WW / RUN;                 // runs per window row
     static constexpr int NRUNS = RPR * WH;
     static constexpr int RPL = (NRUNS + 31) / 32;        // runs per lane
     static constexpr int RW = WW + 3, RH = WH + 3;
-    static constexpr int RWW = (RW + 3 + 3) / 4;                      // words per raw row incl. up to 3 bytes of alignment slack
+    // x origin of every staged block is a multiple of XAL bytes: 4 for the word loaders; 16 for TMA (the innermost box
+    // coordinate of a uint8 tensor must be a multiple of 16 bytes -- measured: any other value raises an illegal-instruction fault)
+    static constexpr bool TMA_ = TMA;
+    static constexpr int XSH = TMA ? 4 : 2, XAL = 1 << XSH;
+    static constexpr int RWW0 = (RW + (XAL - 1) + 3) / 4;             // words per raw row incl. the alignment slack
+    static constexpr int RWW = TMA ? ((RWW0 + 3) / 4) * 4 : RWW0;
     static constexpr int RWP = RWW * 4;                               // raw pitch (bytes)
     static constexpr int RAW_LPR = RWW <= 8 ? 8 : 16;                 // lanes per raw row (power of two)
     static constexpr int TILE_WPR = TWC_ / 4;
@@ -243,8 +253,10 @@ struct LKT {
     static constexpr int USEG6 = (WW + 2 + 5) / 6;                    // U is produced in runs of 6 values (3 x 64-bit stores)
     static_assert(6 * USEG6 <= UP && UP % 2 == 0, "U pitch");
     static constexpr int DER_ONLY = (DWP * DH * 4 + 15) & ~15, U_BYTES = (UP * UH * 4 + 15) & ~15;
-    static constexpr int DER_BYTES = DER_ONLY > U_BYTES ? DER_ONLY : U_BYTES, TILE_BYTES = (TWC * TH + 15) & ~15;
-    static constexpr int RAW_BYTES = ((RWP * RH + 15) & ~15) + 16;     // + slack: word loaders read up to 2 words past a run
+    static constexpr int AL = TMA ? 128 : 16;
+    static constexpr int DER_BYTES0 = DER_ONLY > U_BYTES ? DER_ONLY : U_BYTES;
+    static constexpr int DER_BYTES = (DER_BYTES0 + AL - 1) / AL * AL, TILE_BYTES = (TWC * TH + AL - 1) / AL * AL;
+    static constexpr int RAW_BYTES = (RWP * RH + 16 + AL - 1) / AL * AL;     // + slack: word loaders read up to 2 words past a run
     // template patch in shared memory.  A lane owns NPX = RUN * RPL window pixels (q = k * RUN + t); per lane the patch is a
     // list of 32-bit words holding two int16 each: X[i] = (Ix~(2i), Ix~(2i+1)), Y[i] likewise, then I[i] = (I~(2i), I~(2i+1)).
     // Stored chunk-major -- 16-byte chunk c of lane i at (c * 32 + i) * 16 -- so the 128-bit loads of a sweep are conflict-free.
@@ -252,10 +264,12 @@ struct LKT {
     static constexpr int NW_D = 2 * NPAIR, NW_ALL = 3 * NPAIR;
     static constexpr int NCH_D = (NW_D + 3) / 4, NCH_ALL = (NW_ALL + 3) / 4;
     static constexpr int TPL_BYTES = NCH_ALL * 512;
-    static constexpr int PER_WARP = DER_BYTES + TILE_BYTES + 2 * RAW_BYTES + TPL_BYTES;      // raw is double-buffered
+    static constexpr int BAR_BYTES = TMA ? 128 : 0;                   // mbarriers: tile, raw[0], raw[1]
+    static constexpr int PER_WARP = DER_BYTES + TILE_BYTES + 2 * RAW_BYTES + TPL_BYTES + BAR_BYTES;      // raw is double-buffered
+    static_assert(!TMA || (TWC % 16 == 0 && RWP % 16 == 0), "TMA box rows are multiples of 16 bytes");
     static_assert(WW % RUN == 0, "RUN must divide the window width");
     static_assert(AREA <= 2048, "int32 lane partials");
-    static_assert(TWC % 4 == 0 && TWC >= WW + 1 + 2 * MARGIN + 3, "tile pitch");
+    static_assert(TWC % 4 == 0 && TWC >= WW + 1 + 2 * MARGIN + XAL - 1, "tile pitch");
     static_assert(DWP >= DW, "der pitch");
     static_assert(RWW <= 16 && TILE_WPR <= 32, "loader lane mapping");
 };
@@ -310,10 +324,10 @@ template <class T>
 __device__ __forceinline__ void place_tile(int ix, int iy, int W, int H, int &tx0, int &ty0)
 {
     constexpr int WW1 = T::DW, WH1 = T::DH;       // footprint of the window samples
-    tx0 = ((ix - (T::TWC - WW1 - 3) / 2) >> 2) << 2;
+    tx0 = ((ix - (T::TWC - WW1 - (T::XAL - 1)) / 2) >> T::XSH) << T::XSH;
     ty0 = iy - (T::TH - WH1) / 2;
     if (ix >= 0 && ix + WW1 <= W && W >= T::TWC) {
-        const int c = min(max(tx0, 0), ((W - T::TWC) >> 2) << 2);
+        const int c = min(max(tx0, 0), ((W - T::TWC) >> T::XSH) << T::XSH);
         if (ix + WW1 <= c + T::TWC) tx0 = c;           // (alignment can cost up to 3 columns at the right edge)
     }
     if (iy >= 0 && iy + WH1 <= H && H >= T::TH) ty0 = min(max(ty0, 0), H - T::TH);
@@ -325,6 +339,24 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One TMA box (NROWS rows of 4 NWORDS bytes at column gx0, row gy0 of image b) -> dst, completion on mbarrier `bar`.
+// Only boxes inside the level (out-of-bounds elements would be zero-filled, cv2 mirrors) on levels with a tensor map;
+// false: the caller copies with the word loaders.  One lane issues; the proxy fence orders the warp's earlier generic
+// accesses of dst (made visible to that lane by the preceding __syncwarp) before the asynchronous write.
+template <int NROWS, int NWORDS>
+__device__ __forceinline__ bool tma_box(const CUtensorMap *map, bool eligible, int W, int H, int gx0, int gy0, int b, void *dst,
+                                        uint32_t bar, int lane, bool fence = true)
+{
+    if (!(eligible && gx0 >= 0 && gy0 >= 0 && gx0 + 4 * NWORDS <= W && gy0 + NROWS <= H)) return false;     // warp-uniform
+    if (lane == 0) {
+        if (fence) fence_proxy_async();
+        mbar_expect_tx(bar, NROWS * NWORDS * 4);
+        tma_load_3d(smem_u32(dst), map, gx0, gy0, b, bar);
+    }
+    return true;
+}
 
 // Loads NROWS x NWORDS 32-bit words (rows gy0.., columns from the 4-aligned gx0) of a 4-byte aligned plane into `dst`
 // (pitch NWORDS words): LPR lanes per row, 32/LPR rows per pass, all loads issued before the first store (one memory
@@ -384,11 +416,13 @@ __device__ __noinline__ void load_bytes_unaligned(const uint8_t *__restrict__ P,
 
 // `next` tile around (tx0, ty0)
 template <class T>
-__device__ __forceinline__ void load_j_tile(const uint8_t *__restrict__ J, long long rp, int W, int H, bool al4,
+__device__ __noinline__ void load_j_tile(const uint8_t *__restrict__ J, long long rp, int W, int H, bool al4,
                                             int tx0, int ty0, unsigned char *tile, int lane)
 {
     if (al4) {
-        load_words<T::TH, T::TILE_WPR, T::TILE_LPR>(J, rp, W, H, tx0, ty0, reinterpret_cast<uint32_t *>(tile), lane);
+        // (TMA form: this is the fallback of a box that is not inside the level -- the rolled border loader does it all)
+        if constexpr (T::TMA_) load_words_edge<T::TH, T::TILE_WPR, T::TILE_LPR>(J, rp, W, H, tx0, ty0, reinterpret_cast<uint32_t *>(tile), lane);
+        else load_words<T::TH, T::TILE_WPR, T::TILE_LPR>(J, rp, W, H, tx0, ty0, reinterpret_cast<uint32_t *>(tile), lane);
     } else {
         load_bytes_unaligned<T::TH, T::TWC>(J, rp, W, H, tx0, ty0, T::TWC, tile, lane);
     }
@@ -397,12 +431,13 @@ __device__ __forceinline__ void load_j_tile(const uint8_t *__restrict__ J, long 
 // template neighbourhood: rows ipy-1 .. ipy+WH+1, columns from the 4-aligned ax <= ipx-1; returns the byte offset of
 // column ipx-1 inside a raw row (0..3 on the aligned path, 0 on the unaligned path)
 template <class T>
-__device__ __forceinline__ int load_raw(const uint8_t *__restrict__ I, long long rp, int W, int H, bool al4, int ipx, int ipy,
+__device__ __noinline__ int load_raw(const uint8_t *__restrict__ I, long long rp, int W, int H, bool al4, int ipx, int ipy,
                                         unsigned char *raw, int lane)
 {
     if (al4) {
-        const int ax = ((ipx - 1) >> 2) << 2;
-        load_words<T::RH, T::RWW, T::RAW_LPR>(I, rp, W, H, ax, ipy - 1, reinterpret_cast<uint32_t *>(raw), lane);
+        const int ax = ((ipx - 1) >> T::XSH) << T::XSH;
+        if constexpr (T::TMA_) load_words_edge<T::RH, T::RWW, T::RAW_LPR>(I, rp, W, H, ax, ipy - 1, reinterpret_cast<uint32_t *>(raw), lane);
+        else load_words<T::RH, T::RWW, T::RAW_LPR>(I, rp, W, H, ax, ipy - 1, reinterpret_cast<uint32_t *>(raw), lane);
         return (ipx - 1) - ax;
     }
     load_bytes_unaligned<T::RH, T::RWP>(I, rp, W, H, ipx - 1, ipy - 1, T::RW, raw, lane);
@@ -486,15 +521,20 @@ __device__ __noinline__ void template_border(const unsigned char *raw, int ro, s
     __syncwarp();
 }
 
-template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, int MINB>
+constexpr int LKT_TMA_LEVELS = 4;
+struct LKMaps { CUtensorMap prev[LKT_TMA_LEVELS], next[LKT_TMA_LEVELS]; };      // (W, H, B) uint8 planes of the levels
+struct LKNoMaps { int unused; };
+
+template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, int MINB, bool TMA, class MAPS>
 __global__ void __launch_bounds__(LKT_WARPS * 32, MINB)
 k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, double min_eig_thr,
              const float *__restrict__ prev_pts, const int *__restrict__ counts, int max_pts,
              float *__restrict__ next_pts, uint8_t *__restrict__ status, float *__restrict__ err,
-             int *__restrict__ iters_out, unsigned al4_mask, unsigned ial4_mask)
+             int *__restrict__ iters_out, unsigned al4_mask, unsigned ial4_mask, const __grid_constant__ MAPS maps,
+             unsigned tma_mask)
 {
-    using T = LKT<WW, WH, RUN, MARGIN, DWP_, TWC_>;
-    extern __shared__ __align__(16) unsigned char smem_all[];
+    using T = LKT<WW, WH, RUN, MARGIN, DWP_, TWC_, TMA>;
+    extern __shared__ __align__(128) unsigned char smem_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pt = blockIdx.x * LKT_WARPS + warp, b = blockIdx.y;
     const int n = counts ? counts[b] : max_pts;
@@ -505,6 +545,19 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
     unsigned char *tile = uni + T::DER_BYTES;                // `next` tile (prefetched at level entry)
     unsigned char *raw_buf = tile + T::TILE_BYTES;          // raw[l & 1]: template neighbourhood of level l (prefetched one level ahead)
     unsigned char *tpl = raw_buf + 2 * T::RAW_BYTES;        // template patch (layout: LKT)
+    // TMA form: mbarriers 0 = tile, 1 / 2 = raw[0] / raw[1]; `pend` bit k: a TMA copy into buffer k is in flight,
+    // bit 3 + k: a word-loader (cp.async) copy is; `phase` bit k: parity of barrier k's next completion
+    const uint32_t bar0 = TMA ? smem_u32(tpl + T::TPL_BYTES) : 0u;
+    unsigned pend = 0, phase = 0;
+    if constexpr (TMA) {
+        if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 1); fence_mbar_init(); }
+        __syncwarp();
+    }
+    auto wait_buf = [&](int k) {            // TMA form only
+        if (pend & (1u << k)) { mbar_wait(bar0 + 8 * k, (phase >> k) & 1u); phase ^= 1u << k; }
+        else if (pend & (8u << k)) cp_async_wait_all();
+        pend &= ~(9u << k);
+    };
 
     // this lane's runs: (row, first column) -- compile-time count, runtime validity
     int run_y[T::RPL], run_x[T::RPL], run_off[T::RPL];
@@ -542,10 +595,32 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
         const float sc = __int_as_float((127 - l) << 23);          // 2^-l, exact
         const float px = __fsub_rn(__fmul_rn(ppx, sc), hx), py = __fsub_rn(__fmul_rn(ppy, sc), hy);
         const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
-        if (!out_of_level(px, py, ipx, ipy, WW, WH, lv.W[l], lv.H[l]))
-            load_raw<T>(lv.prev[l] + (long long)b * lv.pip[l], lv.prp[l], lv.W[l], lv.H[l], (ial4_mask >> l) & 1u, ipx, ipy,
-                        raw_buf + (l & 1) * T::RAW_BYTES, lane);
-        cp_async_commit();
+        if (!out_of_level(px, py, ipx, ipy, WW, WH, lv.W[l], lv.H[l])) {
+            if constexpr (TMA) {
+                const int k = 1 + (l & 1);
+                if (tma_box<T::RH, T::RWW>(&maps.prev[l], (tma_mask >> l) & 1u, lv.W[l], lv.H[l], ((ipx - 1) >> T::XSH) << T::XSH, ipy - 1, b,
+                                           raw_buf + (l & 1) * T::RAW_BYTES, bar0 + 8 * k, lane, !(tma_mask >> 31)))
+                    pend |= 1u << k;
+                else {
+                    load_raw<T>(lv.prev[l] + (long long)b * lv.pip[l], lv.prp[l], lv.W[l], lv.H[l], (ial4_mask >> l) & 1u, ipx, ipy,
+                                raw_buf + (l & 1) * T::RAW_BYTES, lane);
+                    pend |= 8u << k;
+                }
+            } else
+                load_raw<T>(lv.prev[l] + (long long)b * lv.pip[l], lv.prp[l], lv.W[l], lv.H[l], (ial4_mask >> l) & 1u, ipx, ipy,
+                            raw_buf + (l & 1) * T::RAW_BYTES, lane);
+        }
+        if constexpr (!TMA) cp_async_commit();
+    };
+    // `next` tile at (tx0, ty0) of level l
+    auto issue_tile = [&](int l, const uint8_t *J, long long jrp, int W, int H, bool jal4, int tx0, int ty0) {
+        if constexpr (TMA) {
+            if (tma_box<T::TH, T::TILE_WPR>(&maps.next[l], (tma_mask >> (8 + l)) & 1u, W, H, tx0, ty0, b, tile, bar0, lane, !(tma_mask >> 31))) pend |= 1u;
+            else { load_j_tile<T>(J, jrp, W, H, jal4, tx0, ty0, tile, lane); pend |= 8u; }
+        } else {
+            load_j_tile<T>(J, jrp, W, H, jal4, tx0, ty0, tile, lane);
+            cp_async_commit();
+        }
     };
     issue_raw(n_levels - 1);
     bool tile_pending = false;
@@ -556,9 +631,12 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
         const long long jrp = lv.nrp[l];
         const bool jal4 = (al4_mask >> l) & 1u, ial4 = (ial4_mask >> l) & 1u;
         unsigned char *raw = raw_buf + (l & 1) * T::RAW_BYTES;
-        if (tile_pending) { cp_async_wait<0>(); tile_pending = false; }     // a level left early: its tile copy must land first
+        if (tile_pending) {                                                  // a level left early: its tile copy must land first
+            if constexpr (TMA) wait_buf(0); else cp_async_wait<0>();
+            tile_pending = false;
+        }
         __syncwarp();
-        if (l > 0) issue_raw(l - 1); else cp_async_commit();
+        if (l > 0) issue_raw(l - 1); else if constexpr (!TMA) cp_async_commit();
         const float sc = __int_as_float((127 - l) << 23);          // 2^-l, exact
         float px = __fmul_rn(ppx, sc), py = __fmul_rn(ppy, sc);
         float nx, ny;
@@ -581,14 +659,13 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
         {
             const float fx = __fsub_rn(nx, hx), fy = __fsub_rn(ny, hy);
             place_tile<T>(__float2int_rd(fx), __float2int_rd(fy), W, H, tx0, ty0);
-            load_j_tile<T>(J, jrp, W, H, jal4, tx0, ty0, tile, lane);
-            cp_async_commit();
+            issue_tile(l, J, jrp, W, H, jal4, tx0, ty0);
             tile_pending = true;
         }
         // 1. raw (WW+3)x(WH+3) neighbourhood of prev: issued one level ago; the two newest groups (next level's raw,
         //    this level's tile) may still be in flight
-        const int ro = ial4 ? (ipx - 1) - (((ipx - 1) >> 2) << 2) : 0;
-        cp_async_wait<2>();
+        const int ro = ial4 ? (ipx - 1) - (((ipx - 1) >> T::XSH) << T::XSH) : 0;
+        if constexpr (TMA) wait_buf(1 + (l & 1)); else cp_async_wait<2>();
         __syncwarp();
         // lane partials of the structure tensor and of c = sum I~ * (Ix~, Iy~): the mismatch vector of an iteration is
         // b = sum J~ * (Ix~, Iy~) - c, so a sweep never touches I~
@@ -693,7 +770,7 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
         D = __fdiv_rn(1.f, D);
         nx = __fsub_rn(nx, hx); ny = __fsub_rn(ny, hy);
         float pdx = 0.f, pdy = 0.f;
-        cp_async_wait<0>();          // the `next` tile (and, long since, the next level's raw)
+        if constexpr (TMA) wait_buf(0); else cp_async_wait<0>();          // the `next` tile (and, long since, the next level's raw)
         tile_pending = false;
         __syncwarp();
 
@@ -707,9 +784,8 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
             if (ox < 0 || oy < 0 || ox + WW + 1 > T::TWC || oy + WH + 1 > T::TH) {
                 __syncwarp();
                 place_tile<T>(ix, iy, W, H, tx0, ty0);
-                load_j_tile<T>(J, jrp, W, H, jal4, tx0, ty0, tile, lane);
-                cp_async_commit();
-                cp_async_wait<0>();
+                issue_tile(l, J, jrp, W, H, jal4, tx0, ty0);
+                if constexpr (TMA) wait_buf(0); else cp_async_wait<0>();
                 __syncwarp();
                 ox = ix - tx0; oy = iy - ty0;
             }
@@ -796,6 +872,11 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
             ev = __fdiv_rn((float)se, (float)(32 * WW * WH));
         }
     }
+    if constexpr (TMA) {          // no bulk copy may still be writing this CTA's shared memory when it exits
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (pend & (1u << k)) wait_buf(k);
+    }
     if (lane == 0) {
         next_pts[2 * pidx] = npx;
         next_pts[2 * pidx + 1] = npy;
@@ -805,21 +886,71 @@ k_lk_track_t(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, do
     }
 }
 
-template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, int MINB>
+// (W, H, B) uint8 tensor map of one pyramid level with box (bw, bh, 1); false if the level cannot be described
+static bool lk_level_map(const lkf_image *im, int bw, int bh, CUtensorMap *map)
+{
+    lkf_encode_tiled_fn enc = encode_tiled();
+    if (!enc || im->width < bw || im->height < bh || !aligned_to(im, 16)) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)im->width, (cuuint64_t)im->height, (cuuint64_t)im->batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)im->row_pitch, (cuuint64_t)(im->batch > 1 ? im->image_pitch : im->row_pitch * im->height)};
+    if (gstr[1] % 16) return false;
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1}, estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, im->data, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// TWC_TMA: tile pitch of the TMA form (0: the window has none).  The TMA form (LKF_LK_TMA=1; OFF by default) needs level 0 of
+// both pyramids describable by a tensor map (16-byte aligned planes and pitches).  Measured on the C2 stage (128 000 features,
+// 21x21, profiles/r02_lk_tma.md): 1000 us against 741 us for the cp.async form, bit-identical outputs.  The bulk copies
+// themselves are cheap; the kernel grows from 2520 to 3184 SASS instructions (40 -> 51 KB: 16-byte aligned box origins need
+// 48-byte pitches and wider realignment, barrier bookkeeping, both loader families) and the warps' `no_instruction` stall
+// share -- already the third largest of the cp.async form -- quadruples: the kernel is instruction-cache bound first.
+template <int WW, int WH, int RUN, int MARGIN, int DWP_, int TWC_, int MINB, int TWC_TMA>
 int launch_lk_t(const LKLevels &lv, int n_levels, int max_count, double eps, const lkf_lk_params *p, const float *prev_pts,
                 const int32_t *pt_counts, int max_pts, float *next_pts, uint8_t *status, float *err, int32_t *iters,
-                unsigned al4_mask, unsigned ial4_mask, int B, cudaStream_t s)
+                unsigned al4_mask, unsigned ial4_mask, int B, cudaStream_t s, const lkf_image *prev_pyr, const lkf_image *next_pyr)
 {
+    dim3 grid((max_pts + LKT_WARPS - 1) / LKT_WARPS, B);
+    if constexpr (TWC_TMA > 0) {
+        static const int use_tma = getenv("LKF_LK_TMA") ? atoi(getenv("LKF_LK_TMA")) : 0;
+        if (use_tma && n_levels <= LKT_TMA_LEVELS) {
+            using T = LKT<WW, WH, RUN, MARGIN, DWP_, TWC_TMA, true>;
+            LKMaps maps;
+            unsigned tma_mask = 0;
+            for (int l = 0; l < n_levels; l++) {
+                if (lk_level_map(&prev_pyr[l], T::RWP, T::RH, &maps.prev[l])) tma_mask |= 1u << l;
+                else memset(&maps.prev[l], 0, sizeof(CUtensorMap));
+                if (lk_level_map(&next_pyr[l], T::TWC, T::TH, &maps.next[l])) tma_mask |= 1u << (8 + l);
+                else memset(&maps.next[l], 0, sizeof(CUtensorMap));
+            }
+            for (int l = n_levels; l < LKT_TMA_LEVELS; l++) { memset(&maps.prev[l], 0, sizeof(CUtensorMap)); memset(&maps.next[l], 0, sizeof(CUtensorMap)); }
+            static const int dbg = getenv("LKF_LK_TMA_DBG") ? atoi(getenv("LKF_LK_TMA_DBG")) : 0;      // 1: no raw boxes, 2: no tile boxes
+            const unsigned full_mask = tma_mask;
+            if (dbg & 1) tma_mask &= ~0xffu;
+            if (dbg & 2) tma_mask &= ~0xff00u;
+            if (dbg & 4) tma_mask |= 0x80000000u;      // experiment: no proxy fence before the bulk copies
+            if ((full_mask & 1u) && (full_mask & 0x100u)) {
+                constexpr size_t smem = (size_t)T::PER_WARP * LKT_WARPS;
+                auto kern = k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_TMA, MINB, true, LKMaps>;
+                LKF_FUNC_ATTRS({
+                    LKF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    LKF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                });
+                kern<<<grid, LKT_WARPS * 32, smem, s>>>(lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, prev_pts, pt_counts,
+                                                        max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, maps, tma_mask);
+                return LKF_OK;
+            }
+        }
+    }
     using T = LKT<WW, WH, RUN, MARGIN, DWP_, TWC_>;
     constexpr size_t smem = (size_t)T::PER_WARP * LKT_WARPS;
+    auto kern = k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB, false, LKNoMaps>;
     LKF_FUNC_ATTRS({
-        LKF_CUDA(cudaFuncSetAttribute(k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LKF_CUDA(cudaFuncSetAttribute(k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        LKF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LKF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     });
-    dim3 grid((max_pts + LKT_WARPS - 1) / LKT_WARPS, B);
-    k_lk_track_t<WW, WH, RUN, MARGIN, DWP_, TWC_, MINB><<<grid, LKT_WARPS * 32, smem, s>>>(
-        lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, prev_pts, pt_counts, max_pts, next_pts, status, err, iters,
-        al4_mask, ial4_mask);
+    kern<<<grid, LKT_WARPS * 32, smem, s>>>(lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, prev_pts, pt_counts, max_pts,
+                                            next_pts, status, err, iters, al4_mask, ial4_mask, LKNoMaps{0}, 0u);
     return LKF_OK;
 }
 
@@ -1126,11 +1257,11 @@ LKF_EXPORT int lkf_pyrlk_sparse(lkf_ctx *ctx, const lkf_lk_params *p, int n_leve
     }
     int rc = 1;
     if (p->win_w == 21 && p->win_h == 21)
-        rc = launch_lk_t<21, 21, 7, 1, 22, 28, 28>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<21, 21, 7, 1, 22, 28, 28, 48>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s, prev_pyr, next_pyr);
     else if (p->win_w == 15 && p->win_h == 15)
-        rc = launch_lk_t<15, 15, 5, 1, 17, 24, 24>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<15, 15, 5, 1, 17, 24, 24, 48>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s, prev_pyr, next_pyr);
     else if (p->win_w == 31 && p->win_h == 31)
-        rc = launch_lk_t<31, 31, 31, 1, 33, 44, 16>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s);
+        rc = launch_lk_t<31, 31, 31, 1, 33, 44, 16, 0>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s, prev_pyr, next_pyr);
     else if (p->win_w == 5 && p->win_h == 5)
         rc = launch_lk_small<5, 5>(lv, n_levels, max_count, eps, p, prev_pts, pt_counts, max_pts, next_pts, status, err, iters, al4_mask, ial4_mask, B, s, grid_flag);
     else if (p->win_w == 3 && p->win_h == 3)

@@ -54,6 +54,29 @@ struct DNState {
     int n_next[3];
 };
 
+// (WIN+1) x (WIN+1) bytes of a level at integer origin (ix, iy), REFLECT_101 in both directions, rows packed from byte 0:
+// the border path of the window loader (a column's mirror index is found once, not once per row)
+template <int WIN>
+__device__ __noinline__ void load_window_edge(const uint8_t *__restrict__ P, long long rp, int W, int H, int ix, int iy, uint32_t *out)
+{
+    constexpr int NB = WIN + 1, NW = (NB + 3) / 4;
+    int cx[NB];
+#pragma unroll
+    for (int c = 0; c < NB; c++) cx[c] = reflect101(ix + c, W);
+#pragma unroll 1
+    for (int y = 0; y < NB; y++) {
+        const uint8_t *row = P + (long long)reflect101(iy + y, H) * rp;
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (4 * i + c < NB) v |= (uint32_t)row[cx[4 * i + c]] << (8 * c);
+            out[y * NW + i] = v;
+        }
+    }
+}
+
 template <int WIN, int DN_TH>
 size_t dn_smem_bytes(int n_levels)
 {
@@ -67,12 +90,12 @@ size_t dn_smem_bytes(int n_levels)
     return b;
 }
 
-template <int WIN, int DN_TH>
-__global__ void __launch_bounds__(DN_TW * DN_TH, 1024 / (DN_TW * DN_TH))
+template <int WIN, int DN_TH, int MINB>
+__global__ void __launch_bounds__(DN_TW * DN_TH, MINB)
 k_lk_dense(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, double min_eig_thr,
            float *__restrict__ next_pts, uint8_t *__restrict__ status, float *__restrict__ err,
            int *__restrict__ iters_out, unsigned al4_mask, int map_elems, int sch_elems,
-           const int *__restrict__ grid_flag)
+           const int *__restrict__ grid_flag, int tail)
 {
     using D = DN<WIN, DN_TH>;
     constexpr int DN_NT = DN_TW * DN_TH;
@@ -241,13 +264,12 @@ k_lk_dense(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, doub
                     }
                 }
             } else {
+                uint32_t t[(WIN + 1) * NWJ];
+                load_window_edge<WIN>(J, jrp, W, H, ix, iy, t);
 #pragma unroll
-                for (int y = 0; y <= WIN; y++) {
-                    uint32_t t[NWJ];
-                    load_row_bytes_edge<WIN + 1>(J + (long long)reflect101(iy + y, H) * jrp, W, ix, t);
+                for (int y = 0; y <= WIN; y++)
 #pragma unroll
-                    for (int i = 0; i < NWJ; i++) jr[y][i] = t[i];
-                }
+                    for (int i = 0; i < NWJ; i++) jr[y][i] = t[y * NWJ + i];
             }
         };
         // one Newton iteration of feature f; true if the feature needs another one
@@ -302,10 +324,10 @@ k_lk_dense(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, doub
         };
 
         // C. Newton iterations, one per round; the unfinished features are re-packed after every round (one barrier per
-        //    round: warp-aggregated append to the next list, three rotating counters).  Once a single warp can hold what is
-        //    left, warp 0 finishes those features on its own (no more barriers).
+        //    round: warp-aggregated append to the next list, three rotating counters).  Once `tail` or fewer are left, the
+        //    warps holding them finish their features on their own (no more barriers).
         int round = 0;
-        while (n_act > 32) {                                        // block-uniform
+        while (n_act > tail) {                                      // block-uniform
             bool cont = false;
             int f = 0;
             if (tid < n_act) { f = S.list[cur][tid]; cont = iterate(f); }
@@ -319,8 +341,8 @@ k_lk_dense(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, doub
             n_act = S.n_next[round % 3];
             cur ^= 1; round++;
         }
-        if (wid == 0 && lane < n_act) {
-            const int f = S.list[cur][lane];
+        if (tid < n_act) {
+            const int f = S.list[cur][tid];
             while (iterate(f)) { }
         }
         __syncthreads();
@@ -376,7 +398,7 @@ k_grid_check(const float2 *__restrict__ pts, long long n_total, int W, long long
     if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) *flag = 0;
 }
 
-template <int WIN, int DN_TH>
+template <int WIN, int DN_TH, int MINB>
 int launch_dense(const LKLevels &lv, int n_levels, int max_count, double eps, const lkf_lk_params *p, float *next_pts, uint8_t *status,
                  float *err, int32_t *iters, unsigned al4_mask, int B, const int *grid_flag, cudaStream_t s)
 {
@@ -385,12 +407,14 @@ int launch_dense(const LKLevels &lv, int n_levels, int max_count, double eps, co
     const size_t smem = dn_smem_bytes<WIN, DN_TH>(n_levels);
     if (smem > 227 * 1024) return LKF_ERR_UNSUPPORTED;
     LKF_FUNC_ATTRS({
-        LKF_CUDA(cudaFuncSetAttribute(k_lk_dense<WIN, DN_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dn_smem_bytes<WIN, DN_TH>(DN_MAX_LEVELS)));
-        LKF_CUDA(cudaFuncSetAttribute(k_lk_dense<WIN, DN_TH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        LKF_CUDA(cudaFuncSetAttribute(k_lk_dense<WIN, DN_TH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dn_smem_bytes<WIN, DN_TH>(DN_MAX_LEVELS)));
+        LKF_CUDA(cudaFuncSetAttribute(k_lk_dense<WIN, DN_TH, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     });
+    // rounds are re-packed across the CTA while more than `tail` features are unfinished; then every warp finishes its own
+    static const int tail = getenv("LKF_DN_TAIL") ? atoi(getenv("LKF_DN_TAIL")) : 32;
     dim3 grid((lv.W[0] + DN_TW - 1) / DN_TW, (lv.H[0] + DN_TH - 1) / DN_TH, B);
-    k_lk_dense<WIN, DN_TH><<<grid, DN_NT, smem, s>>>(lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, next_pts, status, err,
-                                              iters, al4_mask, D::map_elems(n_levels), D::sch_elems(n_levels), grid_flag);
+    k_lk_dense<WIN, DN_TH, MINB><<<grid, DN_NT, smem, s>>>(lv, n_levels, max_count, make_eps(eps), p->flags, p->min_eig_threshold, next_pts, status, err,
+                                              iters, al4_mask, D::map_elems(n_levels), D::sch_elems(n_levels), grid_flag, tail);
     return LKF_OK;
 }
 
@@ -428,18 +452,15 @@ int lk_dense_launch(const lkf_lk_params *p, int n_levels, const lkf_image *prev_
         lv.H[l] = prev_pyr[l].height; lv.W[l] = prev_pyr[l].width;
         if (aligned_to(&next_pyr[l], 4)) al4_mask |= 1u << l;
     }
-    static const int th = getenv("LKF_DN_TH") ? atoi(getenv("LKF_DN_TH")) : 8;      // tile height (tuning switch)
-    if (th == 4) {
-        switch (p->win_w) {
-        case 3: return launch_dense<3, 4>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
-        case 5: return launch_dense<5, 4>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
-        case 7: return launch_dense<7, 4>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
-        }
-    }
+    static const int minb = getenv("LKF_DN_MINB") ? atoi(getenv("LKF_DN_MINB")) : 6;      // resident CTAs per SM the registers are capped for (tuning switch)
+#define LKF_DN_ARGS lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s
+    // measured on the C4 frame (1080p, 5x5): 0.903 / 0.848 / 0.847 ms for 4 / 5 / 6 resident CTAs (64 / 48 / 40 registers)
+    if (p->win_w == 5 && minb == 4) return launch_dense<5, 8, 4>(LKF_DN_ARGS);
     switch (p->win_w) {
-    case 3: return launch_dense<3, 8>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
-    case 5: return launch_dense<5, 8>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
-    case 7: return launch_dense<7, 8>(lv, n_levels, max_count, eps, p, next_pts, status, err, iters, al4_mask, B, grid_flag, s);
+    case 3: return launch_dense<3, 8, 6>(LKF_DN_ARGS);
+    case 5: return launch_dense<5, 8, 6>(LKF_DN_ARGS);
+    case 7: return launch_dense<7, 8, 5>(LKF_DN_ARGS);
     }
+#undef LKF_DN_ARGS
     return LKF_ERR_UNSUPPORTED;
 }

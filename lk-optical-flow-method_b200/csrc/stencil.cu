@@ -3,6 +3,7 @@
 // Structure: shared-memory tiles with halos, 4-byte aligned bodies loaded as 32-bit words, REFLECT_101 by
 // index mirroring (the mirror source of a 1..2-px halo is always inside the image).
 #include "common.cuh"
+#include "tma.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -461,27 +462,6 @@ __global__ void __launch_bounds__(SV_NT, 8) k_pyrdown_stream(const uint8_t *__re
 // ---------------------------------------------------------------------------------------------
 constexpr int PT_ROWS = 8, PT_NST = 3, PT_SEG_MAX = 46, PT_STRIP = 1920, PT_MAXW = 4;      // up to 4 consumer warps + 1 producer warp
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int x, int y, int z, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
-}
-
 __global__ void __launch_bounds__((PT_MAXW + 1) * 32, 6)
 k_pyrdown_tma(const __grid_constant__ CUtensorMap map, const uint8_t *__restrict__ src, long long srp, long long sip,
               uint8_t *__restrict__ dst, long long drp, long long dip, int Hs, int Ws, int Hd, int Wd, int n_boxes,
@@ -608,23 +588,6 @@ k_pyrdown_tma(const __grid_constant__ CUtensorMap map, const uint8_t *__restrict
             if (lane == 0) mbar_arrive(empty0 + 8 * st);
         }
     }
-}
-
-typedef CUresult (*lkf_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static lkf_encode_tiled_fn encode_tiled()
-{
-    static lkf_encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (lkf_encode_tiled_fn)p;
-        tried = true;
-    }
-    return fn;
 }
 
 // 1 = launched, 0 = geometry not eligible (caller falls back to the streaming kernel), < 0 = error

@@ -177,3 +177,23 @@ def test_dense_flow_1080p_full_grid(oracle):
     agree, dflow, derr = _compare(sub, ref)
     assert agree >= STATUS_MIN and dflow <= FLOW_TOL and derr <= 1e-2, (agree, dflow, derr)
     assert 0.2 < dense[1].mean() < 1.0                   # a plausible share of pixels is trackable with a 5x5 window
+
+
+def test_tma_form_of_the_warp_tracker_is_bit_identical():
+    """k_lk_track_t has a second form that stages the `next` tile and the template neighbourhood with TMA boxes
+    (cp.async.bulk.tensor + mbarrier; LKF_LK_TMA=1, off by default because it measured slower: profiles/r02_lk_tma.md).
+    The switch is read once per process, so both forms run in child processes on the C2 stage (4 pairs x 2000 features,
+    21x21, 3 levels) and must print the same digest of (nextPts, status, err)."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, LKF_LK_TMA=flag)
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "exp_round.py"), "lk", "4"], env=env, capture_output=True,
+                             text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append(re.search(r"digest (\w+)", out.stdout).group(1))
+    assert digests[0] == digests[1] and digests[0] != "-"
