@@ -762,6 +762,19 @@ def run_b200(args):
                 "peak": hbm_peak, "unit": "GB/s", "frac": stages["process_img"]["frac_of_hbm_peak"],
                 "traffic": step_traffic("k_blur3_stream"), "traffic_source": traffic_src, "peak_source": peak_src}
 
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        # BASELINE.json configs 3 and 4 (parity-test cases, not the bench line): device times with cv2 beside them
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        try:
+            import bench_configs
+            configs = {"c3": bench_configs.c3(), "c4": bench_configs.c4(),
+                       "note": "device-resident inputs, CUDA events, back-to-back repetitions (tools/bench_configs.py); C4 = dense "
+                               "per-pixel LK: `gpu_ms` through lkf_pyrlk_sparse with the raster grid as prevPts (switches to the tiled "
+                               "dense kernel on the device), `gpu_ms_thread_per_feature_kernel` = the same points in reversed order"}
+        except Exception as e:      # the headline line must not depend on the side blocks
+            configs = {"error": repr(e)}
     line = None
     if rank == 0:
         cpu = None
@@ -775,7 +788,7 @@ def run_b200(args):
                 "config": bench_config(B),
                 "timed": "CUDA-graph replay of the whole step, CUDA events on the launch stream; torch.distributed (NCCL) only for "
                          "the barrier and the MAX of the timing, never on the data path",
-                "sustained": sustained, "h2d_pinned": h2d_bw, "dropin": dropin, "c5": c5,
+                "sustained": sustained, "h2d_pinned": h2d_bw, "dropin": dropin, "c5": c5, "configs": configs,
                 "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),
                         "note": "pinned host BGR frames + points -> H2D -> kernels -> D2H tracks, double-buffered copy stream",
@@ -821,6 +834,7 @@ def main():
     ap.add_argument("--sustain-seconds", type=float, default=3.0, help="length of the sustained leg (graph replays)")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 block (64 clips sharded over the ranks, CSV output)")
     ap.add_argument("--no-dropin", action="store_true", help="skip the per-call drop-in latencies (N=1 only)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 timing block (N=1 only)")
     ap.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_worker:
