@@ -102,3 +102,34 @@ def test_gftt_against_cv2_when_available(oracle):
     got = cv.goodFeaturesToTrack(prev, **fp)
     ref = cv2.goodFeaturesToTrack(prev, **fp)
     assert np.array_equal(got, ref)
+
+
+def _same_as_oracle(oracle, img, **fp):
+    import lk_optical_flow_method_b200.cv as cv
+    got = cv.goodFeaturesToTrack(img, mask=None, **fp)
+    ref = oracle.good_features_to_track(img, fp["maxCorners"], fp["qualityLevel"], fp["minDistance"], blockSize=fp["blockSize"])
+    assert (got is None) == (ref is None)
+    if ref is not None:
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        assert np.array_equal(got, ref)
+    return 0 if ref is None else len(ref)
+
+
+def test_selection_paths_that_leave_the_fast_kernel(oracle):
+    """The rank-by-bin selection kernel (k_sort_select_fast) hands lists it cannot finish to the general bitonic-sort kernel:
+    (i) thousands of EXACTLY equal scores (one histogram bin holds them all: ties broken by raster index),
+    (ii) more kept candidates than its shared memory ranks (maxCorners = 12 000 -> 18 256 to keep),
+    (iii) the kept strongest candidates do not yield maxCorners corners under a large minDistance (full list needed).
+    Each must still give the oracle's list, order included."""
+    t = np.zeros((512, 640), np.uint8)
+    t[4::8, 4::8] = 255                                          # 64 x 80 identical corners
+    n = _same_as_oracle(oracle, t, maxCorners=3000, qualityLevel=0.5, minDistance=1, blockSize=3)
+    assert n == 3000
+    n = _same_as_oracle(oracle, t, maxCorners=0, qualityLevel=0.5, minDistance=3, blockSize=3)
+    assert n > 3000
+    prev, _ = processed_pair(1920, 1080)
+    n = _same_as_oracle(oracle, prev, maxCorners=12000, qualityLevel=0.0001, minDistance=1, blockSize=3)
+    assert n == 12000
+    prev, _ = processed_pair(860, 483)
+    n = _same_as_oracle(oracle, prev, maxCorners=300, qualityLevel=0.001, minDistance=40, blockSize=3)
+    assert 50 < n < 300                                          # fewer than maxCorners exist at that spacing
