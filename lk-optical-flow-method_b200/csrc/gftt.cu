@@ -558,11 +558,13 @@ k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int 
         }
     }
     if (!__syncthreads_or(mx != 0)) return;               // (also orders the zeroing of s_cnt)
+    // (few threads hold a maximum: the per-list work below loops over the set bits only)
     auto value = [&](int bit) -> float {
-        const float4 q = cq[bit >> 2];
-        const int j = bit & 3;
+        const int r = bit >> 2, j = bit & 3;
+        const float4 q = r == 0 ? cq[0] : (r == 1 ? cq[1] : (r == 2 ? cq[2] : cq[3]));
         return j == 0 ? q.x : (j == 1 ? q.y : (j == 2 ? q.z : q.w));
     };
+    static_assert(NMS4_ROWS == 4, "value() selects among four rows");
     // per list: the pixels that pass its threshold and mask; slots inside the CTA's block of the list
     unsigned cb[MAXM];
     int ofs[MAXM];
@@ -570,18 +572,19 @@ k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int 
     for (int m = 0; m < MAXM; m++) {
         if (m >= n_masks) break;
         cb[m] = 0; ofs[m] = 0;
-        const int list = b * n_masks + m;
-#pragma unroll
-        for (int bit = 0; bit < 4 * NMS4_ROWS; bit++) {
-            if (!((mx >> bit) & 1u)) continue;
-            bool cand = value(bit) > thr_m[m];
-            if (cand && ms.p) {
-                const int y = ybase + 8 * (bit >> 2), x = x0 + (bit & 3);
-                cand = ms.p[(long long)(ms.per_image ? list : m) * ms.ip + (long long)y * ms.rp + x] != 0;
+        if (mx) {
+            const int list = b * n_masks + m;
+            for (unsigned rest = mx; rest; rest &= rest - 1) {
+                const int bit = __ffs(rest) - 1;
+                bool cand = value(bit) > thr_m[m];
+                if (cand && ms.p) {
+                    const int y = ybase + 8 * (bit >> 2), x = x0 + (bit & 3);
+                    cand = ms.p[(long long)(ms.per_image ? list : m) * ms.ip + (long long)y * ms.rp + x] != 0;
+                }
+                if (cand) cb[m] |= 1u << bit;
             }
-            if (cand) cb[m] |= 1u << bit;
+            if (cb[m]) ofs[m] = atomicAdd(&s_cnt[m], __popc(cb[m]));
         }
-        if (cb[m]) ofs[m] = atomicAdd(&s_cnt[m], __popc(cb[m]));
     }
     __syncthreads();
     if ((int)threadIdx.x < n_masks && s_cnt[threadIdx.x] > 0)
@@ -593,9 +596,8 @@ k_nms_compact4(const float *__restrict__ eig, long long erp, long long eip, int 
         if (!cb[m]) continue;
         const int list = b * n_masks + m;
         int pos = s_base[m] + ofs[m];
-#pragma unroll
-        for (int bit = 0; bit < 4 * NMS4_ROWS; bit++) {
-            if (!((cb[m] >> bit) & 1u)) continue;
+        for (unsigned rest = cb[m]; rest; rest &= rest - 1) {
+            const int bit = __ffs(rest) - 1;
             const int y = ybase + 8 * (bit >> 2), x = x0 + (bit & 3);
             const unsigned k = f2key(value(bit));
             if (pos < cap) keys[(long long)list * cap + pos] = ((unsigned long long)k << 32) | (unsigned)(y * W + x);
