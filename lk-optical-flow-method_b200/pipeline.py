@@ -204,12 +204,16 @@ class HostFeeder:
 
     H2D copies run on a dedicated copy stream into one of two device input slots while the previous
     step computes (double buffering); results return through pinned buffers (also two slots, so the
-    tuple returned for step k is valid until step k+2 is issued)."""
+    tuple returned for step k is valid until step k+2 is issued).  The D2H copies run on a third stream: the
+    compute stream only snapshots the step's results into a device-side slot (a 1.7 MB device copy), so the next
+    step's kernels never wait behind a PCIe transfer."""
 
     def __init__(self, pipe):
         self.pipe = pipe
         p = pipe
         self.copy_stream = torch.cuda.Stream(device=p.dev)
+        self.d2h_stream = torch.cuda.Stream(device=p.dev)
+        self.stage = [tuple(torch.empty_like(t) for t in p.results()) for _ in range(2)]     # device-side snapshots of the results
         self.in_frames = [torch.empty((p.B, p.H, p.W, 3), dtype=torch.uint8, device=p.dev) for _ in range(2)]
         self.in_pts = [torch.empty((p.B, p.N, 2), dtype=torch.float32, device=p.dev) for _ in range(2)]
         self.out = [(torch.empty((p.B, p.N, 2), dtype=torch.float32).pin_memory(),
@@ -225,6 +229,7 @@ class HostFeeder:
         h2d = [torch.cuda.Event() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
         d2h = [torch.cuda.Event() for _ in range(2)]
+        snap = [torch.cuda.Event() for _ in range(2)]
         outs = []
         for k, (frames, pts) in enumerate(batches):
             s = k & 1
@@ -240,10 +245,15 @@ class HostFeeder:
             p.step(self.in_frames[s])
             done[s].record(compute)
             if k >= 2:
-                d2h[s].synchronize()                              # host slot s consumed (step k-2 landed)
-            for dst, src in zip(self.out[s], p.results()):
-                dst.copy_(src, non_blocking=True)
-            d2h[s].record(compute)
+                d2h[s].synchronize()                              # host slot s consumed (step k-2 landed): its device snapshot is free too
+            for dst, src in zip(self.stage[s], p.results()):
+                dst.copy_(src)
+            snap[s].record(compute)
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(snap[s])
+                for dst, src in zip(self.out[s], self.stage[s]):
+                    dst.copy_(src, non_blocking=True)
+                d2h[s].record(self.d2h_stream)
             outs.append(self.out[s])
         for e in d2h:
             e.synchronize()
