@@ -105,3 +105,32 @@ def test_dense_rejects_what_it_does_not_cover():
     ppyr, npyr = _pyramids(prev, nxt, (5, 5), 2)
     with pytest.raises(LkfError):
         ops.pyrlk_dense(ppyr, npyr, ops.lk_params_struct((5, 5), 2, (3, 10, 0.03), 4))      # OPTFLOW_USE_INITIAL_FLOW
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_dense_kernel_random_sweep(seed):
+    """seeded sweep of frame sizes (tiny, odd, not multiples of the 32 x 8 tile), windows, level counts, criteria and batch
+    sizes: the tiled kernel against the thread-per-feature kernel on the same grid points (reversed order), bit for bit"""
+    import torch
+    from lk_optical_flow_method_b200 import ops
+    rng = np.random.default_rng(1000 + seed)
+    W = int(rng.choice([17, 33, 64, 95, 130, 257])) + int(rng.integers(0, 4))
+    H = int(rng.choice([9, 16, 31, 50, 77])) + int(rng.integers(0, 4))
+    win = int(rng.choice([3, 5, 7]))
+    ml = int(rng.integers(0, 4))
+    crit = [(3, 10, 0.03), (3, 30, 0.01), (1, 3, 0.0), (2, 0, 0.2), (3, 1, 0.5)][int(rng.integers(0, 5))]
+    B = int(rng.integers(1, 4))
+    flags = 8 if rng.random() < 0.25 else 0
+    prevs, nxts = [], []
+    for b in range(B):
+        p, n = processed_pair(W, H, seed=int(rng.integers(0, 3)), t0=int(rng.integers(1, 9)))
+        prevs.append(p); nxts.append(n)
+    ppyr, npyr = _pyramids(np.stack(prevs), np.stack(nxts), (win, win), ml)
+    params = ops.lk_params_struct((win, win), ml, crit, flags)
+    dn, ds, de, di = [t.cpu().numpy() for t in ops.pyrlk_dense(ppyr, npyr, params, want_iters=True)]
+    g = torch.from_numpy(_grid(W, H)[::-1].copy()).cuda()[None].repeat(B, 1, 1).contiguous()
+    sn, ss, se, si = [t.cpu().numpy() for t in ops.pyrlk(ppyr, npyr, g, params, want_iters=True)]
+    for b in range(B):
+        assert np.array_equal(dn[b], sn[b][::-1]), (W, H, win, ml, crit, B)
+        assert np.array_equal(ds[b], ss[b][::-1]) and np.array_equal(di[b], si[b][::-1])
+        assert np.array_equal(de[b].view(np.uint32), se[b][::-1].view(np.uint32))
