@@ -4,6 +4,7 @@ Use at the reference's call sites as  ``import lk_optical_flow_method_b200.cv as
 ``patch(cv2)`` to swap the four functions inside an already imported cv2 module).  Same names,
 argument meaning, return conventions and error behaviour as the cv2 functions the scripts call:
 
+    resize(frame, (w, h), interpolation=INTER_AREA)                via imutils.resize, VP.py:433,531 (everything else -> cv2)
     cvtColor(img, COLOR_BGR2GRAY)                                  VP.py:406   LKF.py:402
     GaussianBlur(img, (3,3), 0)                                    VP.py:420   LKF.py:416
     goodFeaturesToTrack(img, mask=..., **feature_params)           VP.py:503,707  LKF.py:488,691
@@ -44,6 +45,7 @@ OPTFLOW_USE_INITIAL_FLOW = 4
 OPTFLOW_LK_GET_MIN_EIGENVALS = 8
 BORDER_DEFAULT = 4
 BORDER_REFLECT_101 = 4
+INTER_AREA = 3
 
 
 try:                                    # after patch(cv2) a script's `except cv2.error` must still catch our argument errors
@@ -215,6 +217,30 @@ def cvtColor(src, code, dst=None, dstCn=0):
     return _register(_back(g, src), g)
 
 
+def resize(src, dsize, dst=None, fx=0, fy=0, interpolation=1):
+    """cv2.resize.  The call the scripts make through imutils.resize(frame, width=860) -- INTER_AREA, uint8, a non-integer
+    down-scale in both axes (1280x720 -> 860x483, VP.py:433,531) -- runs on the B200 (lkf_resize_area_u8, bit-exact);
+    every other use (other interpolations, enlargements, integer factors, other dtypes) is forwarded to cv2 unchanged."""
+    ok = interpolation == INTER_AREA and dsize is not None and len(tuple(dsize)) == 2 and fx == 0 and fy == 0 and dst is None
+    if ok:
+        shape, dt = tuple(src.shape), src.dtype
+        Wd, Hd = int(dsize[0]), int(dsize[1])
+        ok = (dt in (np.uint8, torch.uint8) and len(shape) in (2, 3) and (len(shape) == 2 or shape[2] == 3) and
+              0 < Wd < shape[1] and 0 < Hd < shape[0] and not (shape[1] % Wd == 0 and shape[0] % Hd == 0))
+    if not ok:
+        import cv2
+        if is_device(src):
+            raise error("resize: only INTER_AREA non-integer down-scaling of uint8 images is implemented for device tensors")
+        return cv2.resize(src, dsize, dst=dst, fx=fx, fy=fy, interpolation=interpolation)
+    try:
+        if is_device(src):
+            return ops.resize_area(src, (Wd, Hd))[0]
+        r = ops.resize_area(_to_dev(as_host_array(src)), (Wd, Hd))[0]
+    except LkfError as e:
+        raise error(str(e)) from e
+    return _register(_back(r, src), r)
+
+
 def GaussianBlur(src, ksize, sigmaX, dst=None, sigmaY=0, borderType=BORDER_DEFAULT):
     """cv2.GaussianBlur for ksize == (3,3), sigma == 0, BORDER_DEFAULT (VP.py:420)."""
     if tuple(ksize) != (3, 3) or sigmaX != 0 or sigmaY != 0 or borderType != BORDER_DEFAULT:
@@ -352,9 +378,10 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status=None, err=No
 
 
 def patch(cv2_module):
-    """Replace the four hot-path functions inside an imported cv2 module (returns the originals)."""
+    """Replace the hot-path functions inside an imported cv2 module (returns the originals): the four calls of SURVEY 8b
+    and cv2.resize, which imutils.resize reaches with INTER_AREA (f1; other resize uses fall through to the original)."""
     saved = {}
-    for name in ("cvtColor", "GaussianBlur", "goodFeaturesToTrack", "calcOpticalFlowPyrLK"):
+    for name in ("cvtColor", "GaussianBlur", "goodFeaturesToTrack", "calcOpticalFlowPyrLK", "resize"):
         saved[name] = getattr(cv2_module, name)
         setattr(cv2_module, name, globals()[name])
     return saved

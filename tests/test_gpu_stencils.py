@@ -97,3 +97,36 @@ def test_against_cv2_when_available(oracle):
     s = ops.scharr(out)[0].cpu().numpy()
     assert np.array_equal(s[..., 0], cv2.Scharr(g, cv2.CV_16S, 1, 0))
     assert np.array_equal(s[..., 1], cv2.Scharr(g, cv2.CV_16S, 0, 1))
+
+
+def test_cv_resize_dropin_is_cv2_resize():
+    """cv.resize (what imutils.resize calls, VP.py:433,531): INTER_AREA non-integer down-scales of uint8 frames run on the GPU
+    and equal cv2.resize byte for byte; every other use is forwarded to cv2; patch(cv2) swaps it in."""
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    import lk_optical_flow_method_b200.cv as cv
+    from lk_optical_flow_method_b200.device import Workspace
+    from conftest import synth_frames
+    lib = Workspace.current().lib
+    for (W, H) in ((1280, 720), (1920, 1080)):
+        f = synth_frames(W, H, 1)[0]
+        n0 = lib.lkf_ctx_launch_count(None)
+        got = cv.resize(f, (860, 483), interpolation=cv2.INTER_AREA)
+        assert lib.lkf_ctx_launch_count(None) > n0                                   # the CUDA kernel ran
+        assert got.dtype == np.uint8 and np.array_equal(got, cv2.resize(f, (860, 483), interpolation=cv2.INTER_AREA))
+        g = np.ascontiguousarray(f[..., 1])
+        assert np.array_equal(cv.resize(g, (430, 241), interpolation=cv2.INTER_AREA), cv2.resize(g, (430, 241), interpolation=cv2.INTER_AREA))
+    d = cv.resize(torch.from_numpy(f).cuda(), (860, 483), interpolation=cv2.INTER_AREA)  # device in -> device out
+    assert d.is_cuda and np.array_equal(d.cpu().numpy(), cv2.resize(f, (860, 483), interpolation=cv2.INTER_AREA))
+    n0 = lib.lkf_ctx_launch_count(None)
+    assert np.array_equal(cv.resize(f, (960, 540), interpolation=cv2.INTER_AREA), cv2.resize(f, (960, 540), interpolation=cv2.INTER_AREA))  # integer factor
+    assert np.array_equal(cv.resize(f, (860, 483)), cv2.resize(f, (860, 483)))          # INTER_LINEAR
+    assert np.array_equal(cv.resize(f, None, fx=0.5, fy=0.5), cv2.resize(f, None, fx=0.5, fy=0.5))
+    assert lib.lkf_ctx_launch_count(None) == n0                                       # all three went to cv2
+    saved = cv.patch(cv2)
+    try:
+        assert cv2.resize is cv.resize
+        assert np.array_equal(cv2.resize(f, (860, 483), interpolation=cv2.INTER_AREA), got)
+    finally:
+        cv.unpatch(cv2, saved)
+    assert cv2.resize is not cv.resize
