@@ -13,13 +13,29 @@ from . import _lib
 from ._lib import LkfImage, check
 
 
+_cuda_ok = False
+
+
 def require_cuda():
+    """Raises without a CUDA device (no CPU fallback).  The positive answer is remembered: torch.cuda.is_available() costs
+    ~4 us and sits on every per-call path of the drop-in functions."""
+    global _cuda_ok
+    if _cuda_ok:
+        return
     if not torch.cuda.is_available():
         raise RuntimeError("lk_optical_flow_method_b200 needs a CUDA device (B200, sm_100a); "
                            "there is no CPU fallback")
+    _cuda_ok = True
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (the raw-handle query: 14 us less per call than
+    building a torch.cuda.Stream object)."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -32,6 +48,12 @@ def image_desc(t, channels=1):
     if not t.is_cuda:
         raise ValueError("expected a CUDA tensor")
     es = _ELEM[t.dtype]
+    nd = t.dim()
+    if t.is_contiguous() and ((channels == 1 and nd == 3) or (channels > 1 and nd == 4 and t.shape[3] == channels)):
+        # the common case on the per-call paths: dense planes, pitches follow from the shape (no stride queries)
+        B, H, W = t.shape[0], t.shape[1], t.shape[2]
+        rp = W * channels * es
+        return LkfImage(t.data_ptr(), B, H, W, channels, rp, rp * H)
     if channels == 1:
         if t.dim() == 2:
             t = t.unsqueeze(0)
