@@ -99,3 +99,19 @@ def test_csv_text_equals_csv_writer_on_edge_values():
     assert V.csv_text(rows) == V.csv_text_reference(rows)
     assert V.csv_text(np.zeros((0, 2))) == V.csv_text_reference([]) == "x,y\r\n"
     assert V.csv_text([(1.5, 2.0)]) == "x,y\r\n1.5,2.0\r\n"
+
+
+def test_cv_resize_forwards_everything_but_the_area_downscale():
+    """cv.resize sends every use except the INTER_AREA non-integer uint8 down-scale to cv2 (no CUDA needed for those)."""
+    cv2 = pytest.importorskip("cv2")
+    import lk_optical_flow_method_b200.cv as cv
+    a = np.random.default_rng(0).integers(0, 255, (72, 128, 3), dtype=np.uint8)
+    assert cv.INTER_AREA == cv2.INTER_AREA
+    for args, kw in [(((64, 36),), dict(interpolation=cv2.INTER_AREA)),          # integer factor: cv2's fast path
+                     (((100, 50),), {}),                                           # INTER_LINEAR
+                     (((200, 100),), dict(interpolation=cv2.INTER_AREA)),        # enlargement
+                     ((None,), dict(fx=0.5, fy=0.5, interpolation=cv2.INTER_AREA)),
+                     (((100, 50),), dict(interpolation=cv2.INTER_CUBIC))]:
+        assert np.array_equal(cv.resize(a, *args, **kw), cv2.resize(a, *args, **kw))
+    f = a.astype(np.float32)
+    assert np.array_equal(cv.resize(f, (100, 50), interpolation=cv2.INTER_AREA), cv2.resize(f, (100, 50), interpolation=cv2.INTER_AREA))
