@@ -52,6 +52,7 @@ struct DNState {
     unsigned short list[2][DN_NT];
     int warp_cnt[DN_NT / 32];
     int n_next[3];
+    int4 wlut[64];                       // Q14 weights of the (u mod 2^l, v mod 2^l) phases of the current level (<= 8 x 8)
 };
 
 // (WIN+1) x (WIN+1) bytes of a level at integer origin (ix, iy), REFLECT_101 in both directions, rows packed from byte 0:
@@ -88,6 +89,78 @@ size_t dn_smem_bytes(int n_levels)
     b += (size_t)D::sch_elems(n_levels) * 4;              // Scharr tile
     b += ((size_t)D::raw_bytes(n_levels) + 15) & ~(size_t)15;
     return b;
+}
+
+
+// Phase A of a level (kept OUT OF LINE: the kernel's iteration loop is compiled for 40 registers and its allocation is fragile):
+// raw tile of prev -> Scharr tile -> the map M_l of the CTA's tile + halo.  NT threads, three barriers inside.
+template <int WIN, int NT>
+__device__ __noinline__ void dn_build_maps(const uint8_t *__restrict__ I, long long irp, int W, int H, int l, int x0, int y0, int th,
+                                           unsigned char *raw, int *sch, int2 *mapD, unsigned short *mapI, int4 *wlut)
+{
+    constexpr int R = (WIN - 1) / 2;
+    const int tid = threadIdx.x;
+    const int Sd = 1 << l, halo = R << l;
+    const int MW = DN_TW + 2 * halo, MH = th + 2 * halo;
+    const int u0 = x0 - halo, v0 = y0 - halo;                  // map origin in level-0 ("upsampled") coordinates
+    const int i0 = u0 >> l, j0 = v0 >> l;                      // integer sample under the map origin (floor)
+    const int IW = ((u0 + MW - 1) >> l) - i0 + 2, IH = ((v0 + MH - 1) >> l) - j0 + 2;
+    const int RWP = (IW + 2 + 3) & ~3;
+    // (row, column) of a linear index < 65536 without a division: idx / d = (idx * ceil(2^32 / d)) >> 32 for d <= 256
+    auto split = [](int idx, int d, unsigned magic, int &q, int &r) { q = (int)__umulhi((unsigned)idx, magic); r = idx - q * d; };
+    // A1. raw tile of prev: rows j0-1 .. j0+IH, columns i0-1 .. i0+IW (REFLECT_101); the Q14 weights of the level's phases
+    {
+        const unsigned magic = 0xffffffffu / (unsigned)(IW + 2) + 1u;
+        for (int idx = tid; idx < (IW + 2) * (IH + 2); idx += NT) {
+            int j, i;
+            split(idx, IW + 2, magic, j, i);
+            raw[j * RWP + i] = I[(long long)reflect101(j0 - 1 + j, H) * irp + reflect101(i0 - 1 + i, W)];
+        }
+        if (tid < Sd * Sd) {
+            const float sc = __int_as_float((127 - l) << 23);          // 2^-l, exact
+            int w00, w01, w10, w11;
+            weights(__fmul_rn((float)(tid & (Sd - 1)), sc), __fmul_rn((float)(tid >> l), sc), w00, w01, w10, w11);
+            wlut[tid] = make_int4(w00, w01, w10, w11);
+        }
+    }
+    __syncthreads();
+    // A2. Scharr at the integer samples (i0 + a, j0 + c); ZERO outside the level (cv2's zero-bordered derivative image)
+    {
+        const unsigned magic = 0xffffffffu / (unsigned)IW + 1u;
+        for (int idx = tid; idx < IW * IH; idx += NT) {
+            int c, a;
+            split(idx, IW, magic, c, a);
+            const int gx = i0 + a, gy = j0 + c;
+            int sx = 0, sy = 0;
+            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+                const unsigned char *r0 = raw + c * RWP + a, *r1 = r0 + RWP, *r2 = r1 + RWP;
+                sx = 3 * ((int)r0[2] - (int)r0[0]) + 10 * ((int)r1[2] - (int)r1[0]) + 3 * ((int)r2[2] - (int)r2[0]);
+                sy = 3 * ((int)r2[0] - (int)r0[0]) + 10 * ((int)r2[1] - (int)r0[1]) + 3 * ((int)r2[2] - (int)r0[2]);
+            }
+            sch[idx] = (sx & 0xffff) | (sy << 16);
+        }
+    }
+    __syncthreads();
+    // A3. the map: Q14 bilinear samples of I (x32) and of the derivatives at (u, v) * 2^-l
+    {
+        const unsigned magic = 0xffffffffu / (unsigned)MW + 1u;
+        for (int idx = tid; idx < MW * MH; idx += NT) {
+            int mv, mu;
+            split(idx, MW, magic, mv, mu);
+            const int u = u0 + mu, v = v0 + mv;
+            const int a = (u >> l) - i0, c = (v >> l) - j0;
+            const int4 wq = wlut[((v & (Sd - 1)) << l) | (u & (Sd - 1))];
+            const int w00 = wq.x, w01 = wq.y, w10 = wq.z, w11 = wq.w;
+            const unsigned char *r0 = raw + (c + 1) * RWP + a + 1, *r1 = r0 + RWP;
+            const int iv = descale((int)r0[0] * w00 + (int)r0[1] * w01 + (int)r1[0] * w10 + (int)r1[1] * w11, 9);
+            const int d00 = sch[c * IW + a], d01 = sch[c * IW + a + 1], d10 = sch[(c + 1) * IW + a], d11 = sch[(c + 1) * IW + a + 1];
+            const int ixv = descale((int)(short)d00 * w00 + (int)(short)d01 * w01 + (int)(short)d10 * w10 + (int)(short)d11 * w11, 14);
+            const int iyv = descale((d00 >> 16) * w00 + (d01 >> 16) * w01 + (d10 >> 16) * w10 + (d11 >> 16) * w11, 14);
+            mapI[idx] = (unsigned short)iv;
+            mapD[idx] = make_int2(ixv, iyv);
+        }
+    }
+    __syncthreads();
 }
 
 template <int WIN, int DN_TH, int MINB>
@@ -129,50 +202,8 @@ k_lk_dense(LKLevels lv, int n_levels, int max_count, LKEps eps2, int flags, doub
         const bool jal4 = (al4_mask >> l) & 1u;
         const int Sd = 1 << l, halo = R << l;
         const int MW = DN_TW + 2 * halo, MH = DN_TH + 2 * halo;
-        const int u0 = x0 - halo, v0 = y0 - halo;                  // map origin in level-0 ("upsampled") coordinates
-        const int i0 = u0 >> l, j0 = v0 >> l;                      // integer sample under the map origin (floor)
-        const int IW = ((u0 + MW - 1) >> l) - i0 + 2, IH = ((v0 + MH - 1) >> l) - j0 + 2;
-        const int RWP = (IW + 2 + 3) & ~3;
         __syncthreads();                                           // previous level's maps and lists are dead
-
-        // A1. raw tile of prev: rows j0-1 .. j0+IH, columns i0-1 .. i0+IW (REFLECT_101)
-        for (int idx = tid; idx < (IW + 2) * (IH + 2); idx += DN_NT) {
-            const int j = idx / (IW + 2), i = idx - j * (IW + 2);
-            raw[j * RWP + i] = I[(long long)reflect101(j0 - 1 + j, H) * irp + reflect101(i0 - 1 + i, W)];
-        }
-        __syncthreads();
-        // A2. Scharr at the integer samples (i0 + a, j0 + c); ZERO outside the level (cv2's zero-bordered derivative image)
-        for (int idx = tid; idx < IW * IH; idx += DN_NT) {
-            const int c = idx / IW, a = idx - c * IW;
-            const int gx = i0 + a, gy = j0 + c;
-            int sx = 0, sy = 0;
-            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
-                const unsigned char *r0 = raw + c * RWP + a, *r1 = r0 + RWP, *r2 = r1 + RWP;
-                sx = 3 * ((int)r0[2] - (int)r0[0]) + 10 * ((int)r1[2] - (int)r1[0]) + 3 * ((int)r2[2] - (int)r2[0]);
-                sy = 3 * ((int)r2[0] - (int)r0[0]) + 10 * ((int)r2[1] - (int)r0[1]) + 3 * ((int)r2[2] - (int)r0[2]);
-            }
-            sch[idx] = (sx & 0xffff) | (sy << 16);
-        }
-        __syncthreads();
-        // A3. the map: Q14 bilinear samples of I (x32) and of the derivatives at (u, v) * 2^-l
-        {
-            const float sc = __int_as_float((127 - l) << 23);          // 2^-l, exact
-            for (int idx = tid; idx < MW * MH; idx += DN_NT) {
-                const int mv = idx / MW, mu = idx - mv * MW;
-                const int u = u0 + mu, v = v0 + mv;
-                const int a = (u >> l) - i0, c = (v >> l) - j0;
-                int w00, w01, w10, w11;
-                weights(__fmul_rn((float)(u & (Sd - 1)), sc), __fmul_rn((float)(v & (Sd - 1)), sc), w00, w01, w10, w11);
-                const unsigned char *r0 = raw + (c + 1) * RWP + a + 1, *r1 = r0 + RWP;
-                const int iv = descale((int)r0[0] * w00 + (int)r0[1] * w01 + (int)r1[0] * w10 + (int)r1[1] * w11, 9);
-                const int d00 = sch[c * IW + a], d01 = sch[c * IW + a + 1], d10 = sch[(c + 1) * IW + a], d11 = sch[(c + 1) * IW + a + 1];
-                const int ixv = descale((int)(short)d00 * w00 + (int)(short)d01 * w01 + (int)(short)d10 * w10 + (int)(short)d11 * w11, 14);
-                const int iyv = descale((d00 >> 16) * w00 + (d01 >> 16) * w01 + (d10 >> 16) * w10 + (d11 >> 16) * w11, 14);
-                mapI[idx] = (unsigned short)iv;
-                mapD[idx] = make_int2(ixv, iyv);
-            }
-        }
-        __syncthreads();
+        dn_build_maps<WIN, DN_NT>(I, irp, W, H, l, x0, y0, DN_TH, raw, sch, mapD, mapI, S.wlut);
 
         // B. level entry of this thread's feature: structure tensor, min-eigenvalue test, start iterate.
         //    Window pixel (i, j) of feature (tx, ty) is map sample (tx + i 2^l, ty + j 2^l).
